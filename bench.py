@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the JMAC hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Headline workload (BASELINE.json configs[3], "C4"): synthetic KG with 2M entities, 2k relations,
+40M triples (uniform endpoints: no cache reuse, the honest HBM-bound case), d=256, two stacked
+relation-aware GNN layers forward+backward.  One step = one pass of both layers over the whole
+graph; value = layer-edges per second = (2 * E * steps) / time, whole job.
+Also reported on the same line (measured after the headline, not inside its timed region):
+  * "scorer": completion scorer fwd+bwd, B=65536 positives x K=64 negatives, 2 layers of tables;
+  * "roofline": the dominant edge kernel timed alone with CUDA events vs MEASURED_PEAKS.json;
+  * "cpu_baseline": the CPU oracle (port of the reference algorithm) on a bounded sample;
+  * "e2e": the same step through the public module API with HOST (pinned) inputs: H2D of
+    X, R, edge_index, edge_type + plan build + 2 layers fwd+bwd + D2H of the loss, every step.
+--impl reference times the reference algorithm's CPU path (oracle port; /root/reference is pure
+Python and does not exist on the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 256
+FULL = dict(N=2_000_000, R=2_000, E=40_000_000, B=65_536, K=64)
+CPU_SAMPLE = dict(N=50_000, R=2_000, E=1_000_000)      # same mean degree (20) and width as C4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_layer_step(N, R, E, steps, warmup, seed=0):
+    """The reference algorithm (oracle port, un-factored per-edge formulation) on host cores:
+    one RelationAwareLayer forward+backward.  Returns (edges/s, seconds per step, threads)."""
+    import numpy as np
+    import torch
+    from oracle import jmac_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    et = torch.randint(0, R, (E,), generator=g)
+    x = (torch.randn(N, D, generator=g) * 0.1).requires_grad_(True)
+    r = (torch.randn(R, D, generator=g) * 0.1).requires_grad_(True)
+    p = {}
+    for name, shape in (("rel_transform_weight1", (D, D)), ("rel_transform_weight2", (D, D)), ("gcn_weight", (D, D)), ("loop_rel", (1, D)),
+                        ("w_att", (2 * D, D)), ("a_att", (D, 1))):
+        w = torch.empty(*shape)
+        torch.nn.init.xavier_normal_(w, generator=g)
+        p[name] = w.requires_grad_(True)
+    p["bn.weight"] = torch.ones(D, requires_grad=True)
+    p["bn.bias"] = torch.zeros(D, requires_grad=True)
+    gout = torch.randn(N, D, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.relation_aware_layer(p, x, r, ei, et, slope=0.05, bn_state=None, training=True)
+        out.backward(gout)
+        times.append(time.perf_counter() - t0)
+        for v in list(p.values()) + [x, r]:
+            v.grad = None
+    dt = sum(times[warmup:]) / max(steps, 1)
+    return E / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(min(args.warmup, 1), 0)
+    s = CPU_SAMPLE
+    eps, dt, threads = cpu_layer_step(s["N"], s["R"], s["E"], steps, warmup)
+    sample = f"one RelationAwareLayer fwd+bwd on N={s['N']}, E={s['E']}, R={s['R']}, d={D} (uniform, mean degree 20 as C4); per-edge throughput"
+    line = {"impl": "reference", "metric": "gnn_layer_edges_per_s_fwd_bwd", "value": eps, "unit": "edges/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, scale=1.0):
+    w = {k: (int(v * scale) if k in ("N", "E", "B") else v) for k, v in FULL.items()}
+    return {"workload": "C4: synthetic KG, 2M entities, 2k relations, 40M triples (uniform), d=256, 2 stacked relation-aware GNN layers fwd+bwd",
+            "entities": w["N"], "relations": w["R"], "edges": w["E"], "dim": D, "layers": 2, "scorer_batch": w["B"], "negatives": w["K"],
+            "parallelism": f"dst-shard x{n_gpus}" if n_gpus > 1 else "single", "l2_policy": "inputs larger than L2 (tables 2 GB each), no flush"}
+
+
+def event_time(fn, warmup, iters):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters      # ms
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from jmac_b200 import RelationAwareLayer, _lib, functional as JF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    cfg = workload_config(world, args.scale)
+    N, R, E, B, K = cfg["entities"], cfg["relations"], cfg["edges"], cfg["scorer_batch"], cfg["negatives"]
+    hbm_peak, peak_src = peaks()
+
+    gen = torch.Generator(device=dev).manual_seed(0)
+    ei = torch.randint(0, N, (2, E), device=dev, generator=gen)
+    et = torch.randint(0, R, (E,), device=dev, generator=gen)
+    x0 = (torch.randn(N, D, device=dev, generator=gen) * 0.1).requires_grad_(True)
+    rel = (torch.randn(R, D, device=dev, generator=gen) * 0.1).requires_grad_(True)
+    gout = torch.randn(N, D, device=dev, generator=gen)
+    torch.manual_seed(0)
+    largs = SimpleNamespace(leaky_relu_w=0.05, comp_op="sub")
+    layers = [RelationAwareLayer(D, D, rel_dim=D, act=torch.tanh, args=largs).to(dev) for _ in range(2)]
+    params = [p for l in layers for p in l.parameters()] + [x0, rel]
+
+    if world > 1:
+        from jmac_b200 import dist as JD
+        runner = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD)
+        step_fn = lambda: runner.step(x0, rel, gout)
+    else:
+        def step_fn():
+            for p in params:
+                p.grad = None
+            h = layers[0](x0, rel, ei, et)
+            h = layers[1](h, rel, ei, et)
+            h.backward(gout)
+
+    # ---- headline: W warm-up, exactly K timed steps, barrier + sync on both sides, max over ranks
+    for _ in range(args.warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = lib.jmac_launch_count()
+    with ClockSampler(local) as clk:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            step_fn()
+        e.record()
+        torch.cuda.synchronize()
+    launches = int(lib.jmac_launch_count() - n0)
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = 2.0 * E / (ms_per_step * 1e-3)
+
+    line = {"metric": "gnn_layer_edges_per_s_fwd_bwd", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "gpu_launches": launches, "clocks": clk.summary()}
+
+    if rank == 0 and world == 1:
+        # ---- roofline of the edge kernels, each timed alone on the launching stream
+        d = D
+        plan = JF.get_plan(ei, et, N, R + 1)
+        with torch.no_grad():
+            Rp = layers[0].relation_transform(rel)
+            P, Q, S = x0 @ layers[0].w_att[:d], x0 @ layers[0].w_att[d:], Rp @ layers[0].w_att[d:]
+            a = layers[0].a_att.reshape(-1).contiguous()
+            X = x0.detach()
+        agg, lse = torch.empty_like(X), torch.empty(N, device=dev)
+        dP, dXe, dQ = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+        dRp, dS, da = torch.empty_like(Rp), torch.empty_like(Rp), torch.zeros(d, device=dev)
+        rec = int(lib.jmac_edge_record_bytes(d))
+        erec = torch.empty(E * rec, dtype=torch.uint8, device=dev)
+        ptr, st = _lib.ptr, _lib.stream_ptr
+        k_fwd = lambda: _lib.check(lib.jmac_edge_fwd(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), 0.05, d, ptr(agg), ptr(lse), st()))
+        k_dst = lambda: _lib.check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), 0.05, d, ptr(agg), ptr(lse),
+                                                         ptr(gout), ptr(dP), ptr(erec), ptr(da), st()))
+        k_src = lambda: _lib.check(lib.jmac_edge_bwd_src(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(dXe), ptr(dQ), st()))
+        k_rel = lambda: _lib.check(lib.jmac_edge_bwd_rel(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(dRp), ptr(dS), st()))
+        row = d * 4
+        algo = {  # algorithmic HBM bytes per launch
+            "edge_fwd": E * (2 * row + 8) + N * (2 * row + 28),
+            "edge_bwd_dst": E * (2 * row + 8 + rec) + N * (4 * row + 28),
+            "edge_bwd_src": E * (row + 8 + rec) + N * (2 * row + 20),
+            "edge_bwd_rel": E * (row + 8 + rec) + (R + 1) * 2 * row,
+        }
+        kernels = {}
+        for name, fn in (("edge_fwd", k_fwd), ("edge_bwd_dst", k_dst), ("edge_bwd_src", k_src), ("edge_bwd_rel", k_rel)):
+            t = event_time(fn, 3, 10)
+            kernels[name] = {"ms": t, "algo_bytes": algo[name], "GBps": algo[name] / t / 1e6, "frac": algo[name] / t / 1e6 / hbm_peak}
+        top = max(kernels, key=lambda k: kernels[k]["ms"])
+        edge_ms = sum(v["ms"] for v in kernels.values())
+        edge_bytes = sum(v["algo_bytes"] for v in kernels.values())
+        line["roofline"] = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                            "frac": kernels[top]["frac"], "traffic": None, "peak_source": peak_src,
+                            "edge_phase_fwd_bwd": {"ms": edge_ms, "GBps": edge_bytes / edge_ms / 1e6, "frac": edge_bytes / edge_ms / 1e6 / hbm_peak,
+                                                   "edges_per_s": E / (edge_ms * 1e-3)},
+                            "kernels": kernels}
+        del agg, lse, dP, dXe, dQ, erec
+
+        # ---- completion scorer, fwd+bwd, reference batch layout
+        rng = np.random.default_rng(0)
+        hh = torch.from_numpy(np.tile(rng.integers(0, N, B), K + 1)).to(dev)
+        rr = torch.from_numpy(np.tile(rng.integers(0, R, B), K + 1)).to(dev)
+        tt = torch.from_numpy(rng.integers(0, N, (K + 1) * B)).to(dev)
+        e_tabs = [x0.detach().clone().requires_grad_(True), (torch.tanh(x0.detach() * 3)).requires_grad_(True)]
+        r_tabs = [rel.detach().clone().requires_grad_(True), (rel.detach() * 0.5).requires_grad_(True)]
+
+        def scorer_step():
+            for t_ in e_tabs + r_tabs:
+                t_.grad = None
+            loss = JF.transe_margin_loss(e_tabs, r_tabs, hh, rr, tt, B, 5.0)
+            loss.sum().backward()
+        t = event_time(scorer_step, 3, 10)
+        scored = (K + 1) * B
+        sbytes = 2 * 3 * (K + 3) * B * row
+        line["scorer"] = {"metric": "triples_scored_per_s_fwd_bwd", "value": scored / (t * 1e-3), "unit": "triples/s", "ms": t,
+                          "batch": B, "negatives": K, "layers": 2, "algo_GBps": sbytes / t / 1e6, "frac_hbm": sbytes / t / 1e6 / hbm_peak,
+                          "note": "includes zero-filling the two dense [N,d] gradient tables per layer (autograd semantics)"}
+        del e_tabs, hh, rr, tt
+
+        # ---- e2e: HOST inputs every step (pinned), plan rebuilt, result read back
+        h_x, h_r = x0.detach().cpu().pin_memory(), rel.detach().cpu().pin_memory()
+        h_ei, h_et = ei.cpu().pin_memory(), et.cpu().pin_memory()
+        h2d = h_x.numel() * 4 + h_r.numel() * 4 + h_ei.numel() * 8 + h_et.numel() * 8
+
+        def e2e_step():
+            JF.clear_plan_cache()
+            dx = h_x.to(dev, non_blocking=True).requires_grad_(True)
+            dr = h_r.to(dev, non_blocking=True).requires_grad_(True)
+            dei, det = h_ei.to(dev, non_blocking=True), h_et.to(dev, non_blocking=True)
+            for p in params:
+                p.grad = None
+            h = layers[1](layers[0](dx, dr, dei, det), dr, dei, det)
+            loss = (h * gout).sum()
+            loss.backward()
+            return float(loss.item())
+        del ei, et
+        torch.cuda.empty_cache()
+        t = event_time(e2e_step, 1, max(2, min(args.steps, 3)))
+        line["e2e"] = {"value": 2.0 * E / (t * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": t,
+                       "api": "jmac_b200.RelationAwareLayer.forward/backward x2 from pinned host tensors, graph plan rebuilt each step"}
+
+        # ---- CPU baseline: oracle port on a bounded sample
+        if not args.no_cpu:
+            s_ = CPU_SAMPLE
+            eps, dt, threads = cpu_layer_step(s_["N"], s_["R"], s_["E"], 2, 1)
+            line["cpu_baseline"] = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",
+                                    "sample": f"one layer fwd+bwd, N={s_['N']}, E={s_['E']}, R={s_['R']}, d={D}, {dt:.2f} s/step; x2 layers = same edges/s"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N/E/B for debugging (bench numbers need 1.0)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+/*
+ * jmac_b200.h -- C ABI of libjmac_b200.so: hand-written sm_100a CUDA kernels for JMAC's hot path.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types: device pointers are ordinary pointers, `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns 0 on success, a positive cudaError_t value on a CUDA failure, or a
+ *     negative JMAC_E* code on an argument error.  Nothing throws, nothing synchronises the stream
+ *     (except plan creation and the *_host convenience entry points, which say so).
+ *   - all float tables are fp32 row-major; `d` (row width) must be a multiple of 4, 4 <= d <= 512,
+ *     rows 16-byte aligned.  Index inputs that mirror the reference are int64 (torch.LongTensor).
+ *   - the library never allocates through torch; scratch memory lives in the plan / is passed in.
+ *
+ * Each entry point cites the reference code (file:line under the reference tree) it replaces.
+ */
+#ifndef JMAC_B200_H
+#define JMAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMAC_OK 0
+#define JMAC_EINVAL (-1)   /* bad argument (null pointer, d not supported, sizes out of range) */
+#define JMAC_ERANGE (-2)   /* an index in edge_index / edge_type is out of range              */
+#define JMAC_ENOMEM (-3)
+
+const char* jmac_version(void);
+/* Human-readable text for the last non-zero return value on this thread. */
+const char* jmac_last_error(void);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+uint64_t jmac_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph plan: CSR-by-destination (+ by-source and by-relation orderings used by backward).
+ * Replaces the per-call index work of RelationAwareLayer.compute_norm (src/jmac_model.py:99-109)
+ * and the gathers of MessagePassing.propagate (modules/helper/message_passing.py:69-81).  Built
+ * once per edge set; the reference reuses one edge set for thousands of steps (train.py:447-485).
+ *   row = edge_index[0] (aggregation target i), col = edge_index[1] (message source j).
+ *   n_rel = number of relation rows INCLUDING the self-loop row (= rel_emb.size(0) + 1).
+ *   chunk = max edges one warp handles before a segment is split (0 = default 256).
+ * Synchronises `stream` (it needs data-dependent sizes).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jmac_plan jmac_plan;
+
+int jmac_plan_create(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, int64_t E,
+                     int64_t N, int64_t n_rel, int chunk, void* stream, jmac_plan** out);
+int jmac_plan_destroy(jmac_plan* plan);
+/* info[0..7] = E, N, n_rel, chunk, #dst work items, #src work items, #rel work items, max in-degree */
+int jmac_plan_info(const jmac_plan* plan, int64_t info[8]);
+/* Copies (device -> caller's DEVICE buffers, any may be NULL): rowptr[N+1], csr_src[E],
+ * csr_type[E], csr_eid[E] (position -> original edge id), sqrt_deg[N]. */
+int jmac_plan_export(const jmac_plan* plan, int32_t* rowptr, int32_t* csr_src, int32_t* csr_type,
+                     int32_t* csr_eid, float* sqrt_deg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Edge phase of RelationAwareLayer.forward for comp_op='sub'
+ * (src/jmac_model.py:49,56-89 + modules/helper/message_passing.py:4-29), in the factored form
+ *   s_e   = a_att . LeakyReLU(P[i] + Q[j] - S[t]),  P = X W_top, Q = X W_bot, S = R' W_bot
+ *   alpha = softmax over the in-edges of i;  agg[i] = sqrt(deg_i) * sum_e alpha_e (X[j] - R'[t])
+ * (the division by edge_norm = deg^-1/2 of message_passing.py:25-26 is the sqrt(deg) factor).
+ * Outputs: agg[N,d]; lse[N] = log-sum-exp of the logits of each destination (saved for backward).
+ * ------------------------------------------------------------------------------------------ */
+int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S,
+                  const float* Rp, const float* a_att, float leaky_slope, int d, float* agg,
+                  float* lse, void* stream);
+
+/* Bytes per edge of the opaque record buffer `erec` that backward passes share. */
+size_t jmac_edge_record_bytes(int d);
+
+/* Backward, destination pass (atomics-free over the CSR): given G = dL/d agg, recomputes the
+ * logits, writes dP[N,d] (= dL/dP), the per-edge record (alpha*sqrt(deg), ds_e, sign mask of the
+ * LeakyReLU argument) into erec[E*jmac_edge_record_bytes(d)] and ACCUMULATES da_att[d] (caller
+ * zeroes it).  Autograd of src/jmac_model.py:75-76,88 and message_passing.py:24-28. */
+int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* Q, const float* X,
+                      const float* S, const float* Rp, const float* a_att, float leaky_slope, int d,
+                      const float* agg, const float* lse, const float* G, float* dP, void* erec,
+                      float* da_att, void* stream);
+/* Backward, source pass (atomics-free over the by-source ordering): dXe[N,d] = sum over out-edges
+ * of alpha*sqrt(deg)*G[i]  (the x_j gather's gradient, replaces index_put_(accumulate)), and
+ * dQ[N,d] = sum over out-edges of ds_e * a_att * LeakyReLU'(z_e). */
+int jmac_edge_bwd_src(jmac_plan* plan, const float* G, const void* erec, const float* a_att,
+                      float leaky_slope, int d, float* dXe, float* dQ, void* stream);
+/* Backward, relation pass (by-relation ordering): dRp[n_rel,d] -= sum alpha*sqrt(deg)*G[i],
+ * dS[n_rel,d] -= sum ds_e * a_att * LeakyReLU'(z_e).  Tables are overwritten (zeroed inside). */
+int jmac_edge_bwd_rel(jmac_plan* plan, const float* G, const void* erec, const float* a_att,
+                      float leaky_slope, int d, float* dRp, float* dS, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm1d over the N nodes + tanh (src/jmac_model.py:52), split so that a multi-GPU caller can
+ * all-reduce the per-feature sums between the two halves.
+ * ------------------------------------------------------------------------------------------ */
+/* sums[2*d] (double, device): ACCUMULATES sum_x[d], sum_x2[d] of pre[N,d] (caller zeroes). */
+int jmac_bn_stats(const float* pre, int64_t N, int d, double* sums, void* stream);
+/* training != 0: uses sums over n_total rows, writes save_mean[d], save_rstd[d], updates
+ * running_mean/var (unbiased variance, momentum) when they are non-NULL.
+ * training == 0: uses running_mean/var.  out = tanh(gamma * xhat + beta). */
+int jmac_bn_tanh_apply(const float* pre, int64_t N, int d, const double* sums, int64_t n_total,
+                       const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, int training, float* out,
+                       float* save_mean, float* save_rstd, void* stream);
+/* bsums[2*d] (double): ACCUMULATES sum dy[d], sum dy*xhat[d] with dy = gout * (1 - out^2). */
+int jmac_bn_tanh_bwd_stats(const float* gout, const float* out, const float* pre, int64_t N, int d,
+                           const float* mean, const float* rstd, double* bsums, void* stream);
+/* gpre = gamma*rstd*(dy - sum_dy/n - xhat*sum_dyxhat/n) (training) or gamma*rstd*dy (eval);
+ * dgamma[d] = sum dy*xhat, dbeta[d] = sum dy (written from bsums when non-NULL). */
+int jmac_bn_tanh_bwd_apply(const float* gout, const float* out, const float* pre, int64_t N, int d,
+                           const float* mean, const float* rstd, const float* gamma,
+                           const double* bsums, int64_t n_total, int training, float* gpre,
+                           float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Completion scorer: TransE-L1 margin loss of JMAC.completion_loss (src/jmac_model.py:345-374)
+ * on the reference's exact batch layout (train.py:347-352): M = (1+K)*B triples, positives are the
+ * first B, the negative at flat position B + k*B + b is compared with positive b.
+ *   score[l*M + m] = || ent_l[h_m] + rel_l[r_m] - ent_l[t_m] ||_1          (saved for backward)
+ *   loss[l]        = mean_{b,k} max(score_b - score_{B+kB+b}, -margin) + margin
+ * n_layers <= 4 tables are scored in one pass over the indices.
+ * ------------------------------------------------------------------------------------------ */
+int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int n_layers, int d,
+                           const int64_t* h, const int64_t* r, const int64_t* t, int64_t M,
+                           int64_t B, int64_t n_ent, int64_t n_rel, float margin, float* score,
+                           float* loss, void* stream);
+/* ACCUMULATES into d_ent[l][n_ent,d], d_rel[l][n_rel,d] (caller zeroes): gloss[l] * dloss[l]/d. */
+int jmac_transe_margin_bwd(const float* const* ent, const float* const* rel, int n_layers, int d,
+                           const int64_t* h, const int64_t* r, const int64_t* t, int64_t M,
+                           int64_t B, float margin, const float* score, const float* gloss,
+                           float* const* d_ent, float* const* d_rel, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pair cosine: cos[m] = <A[ia_m], B[ib_m]> / (max(|A[ia_m]|,1e-12) max(|B[ib_m]|,1e-12)), the
+ * F.normalize + row-dot of JMAC.alignment_loss_simple / alignment_loss (src/jmac_model.py:243-248,
+ * 268-287).  Backward ACCUMULATES into dA, dB (caller zeroes).
+ * ------------------------------------------------------------------------------------------ */
+int jmac_pair_cos_fwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib,
+                      int64_t M, float* cosv, void* stream);
+int jmac_pair_cos_bwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib,
+                      int64_t M, const float* gcos, float* dA, float* dB, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Link prediction: JMAC.forward_linkpred (src/jmac_model.py:301-313) and the ranking loop of
+ * CompletionEvaluator.test (src/validate.py:50-70).
+ *   dist[b,n] = sum_l || ent_l[e_b] + sign*rel_l[r_b] - ent_l[n] ||_1     (sign=-1 for pred_head)
+ * jmac_l1_dist writes the [B,N] matrix (API parity); jmac_l1_rank never materialises it: it
+ * returns rank_b = 1 + #{n : -dist[b,n] > -dist[b,t_b], n not filtered} where the filter of query b
+ * is filt_idx[filt_ptr[b] .. filt_ptr[b+1]) (NULL = raw setting); the target itself never counts.
+ * ------------------------------------------------------------------------------------------ */
+int jmac_l1_dist(const float* const* ent, const float* const* rel, int n_layers, int d,
+                 const int64_t* e_idx, const int64_t* r_idx, int64_t B, int64_t N, int pred_head,
+                 float* dist, void* stream);
+int jmac_l1_rank(const float* const* ent, const float* const* rel, int n_layers, int d,
+                 const int64_t* e_idx, const int64_t* r_idx, const int64_t* t_idx, int64_t B,
+                 int64_t N, int pred_head, const int64_t* filt_ptr, const int64_t* filt_idx,
+                 int32_t* rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMAC_B200_H */

@@ -1,0 +1,173 @@
+// Shared device/host helpers for libjmac_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/jmac_b200.h"
+
+namespace jmac {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+void count_launch();
+
+#define JMAC_CUDA(expr)                                                                    \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            jmac::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (int)_e;                                                                \
+        }                                                                                  \
+    } while (0)
+
+#define JMAC_ARG(cond)                                                                     \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            jmac::set_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond);          \
+            return JMAC_EINVAL;                                                            \
+        }                                                                                  \
+    } while (0)
+
+// every kernel launch of the library goes through this: error check + launch counter
+#define JMAC_LAUNCH_CHECK()              \
+    do {                                 \
+        jmac::count_launch();            \
+        JMAC_CUDA(cudaGetLastError());   \
+    } while (0)
+
+// A work item of a segmented pass: segment id, [beg,end) in that ordering, and the partial slot
+// (-1 when the segment is handled by exactly one item and can be finalised in place).
+struct __align__(16) Item { int seg, beg, end, slot; };
+// A split segment: segment id, first partial slot, number of slots.
+struct __align__(16) Split { int seg, first, count, pad; };
+
+struct ItemList {
+    Item* items = nullptr;
+    Split* splits = nullptr;
+    int n_items = 0, n_splits = 0, n_slots = 0;
+};
+
+}  // namespace jmac
+
+struct jmac_plan {
+    int64_t E = 0, N = 0, n_rel = 0;
+    int chunk = 256;
+    int max_deg = 0;
+    // by destination (CSR)
+    int *rowptr = nullptr, *csr_src = nullptr, *csr_type = nullptr, *csr_eid = nullptr, *csr_dst = nullptr;
+    float* sqrt_deg = nullptr;
+    // by source
+    int *colptr = nullptr, *csc_pos = nullptr, *csc_dst = nullptr;
+    // by relation
+    int *typptr = nullptr, *typ_pos = nullptr, *typ_dst = nullptr;
+    jmac::ItemList dst_items, src_items, typ_items;
+    // scratch for split segments (partials), grown lazily
+    float* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace jmac {
+
+int plan_scratch(jmac_plan* p, size_t bytes, float** out);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// 128-bit streaming load of a gathered node row (read once per SM: keep it out of L1).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+// 128-bit load of a hot (relation / per-node) row through the read-only path, L1-allocating.
+__device__ __forceinline__ float4 ld_hot(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// vector reduction (no return) -- sm_90+: one 16-byte RED instead of four.
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void fma4(float4& acc, float s, float4 a) {
+    acc.x = fmaf(s, a.x, acc.x); acc.y = fmaf(s, a.y, acc.y); acc.z = fmaf(s, a.z, acc.z); acc.w = fmaf(s, a.w, acc.w);
+}
+
+// A row of d floats held by one warp: lane l owns float4 #(v*32 + l), v < VPL (predicated on d4).
+template <int VPL>
+struct Row {
+    float4 v[VPL];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) v[i] = f4_zero();
+    }
+};
+
+template <int VPL, bool STREAM>
+__device__ __forceinline__ void load_row(Row<VPL>& r, const float* base, int64_t row, int d4, int lane) {
+    const float4* p = reinterpret_cast<const float4*>(base) + row * d4;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        int c = i * 32 + lane;
+        if (c < d4) r.v[i] = STREAM ? ld_stream(p + c) : ld_hot(p + c);
+        else r.v[i] = f4_zero();
+    }
+}
+template <int VPL>
+__device__ __forceinline__ void store_row(const Row<VPL>& r, float* base, int64_t row, int d4, int lane) {
+    float4* p = reinterpret_cast<float4*>(base) + row * d4;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        int c = i * 32 + lane;
+        if (c < d4) p[c] = r.v[i];
+    }
+}
+// grid for a persistent warp-per-item kernel: enough blocks to fill every SM at the kernel's
+// occupancy, never more than the work needs.
+template <typename K>
+inline int persistent_blocks(K kernel, int threads, int n_warp_items) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int wpb = threads / 32;
+    long long want = ((long long)n_warp_items + wpb - 1) / wpb;
+    long long cap = (long long)sm_count() * per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+#endif  // __CUDACC__
+
+// host-side dispatch on the number of float4 per lane
+#define JMAC_DISPATCH_VPL(d, ...)                                   \
+    do {                                                            \
+        int _vpl = ((d) / 4 + 31) / 32;                             \
+        if (_vpl == 1) { constexpr int VPL = 1; __VA_ARGS__; }      \
+        else if (_vpl == 2) { constexpr int VPL = 2; __VA_ARGS__; } \
+        else if (_vpl == 3) { constexpr int VPL = 3; __VA_ARGS__; } \
+        else { constexpr int VPL = 4; __VA_ARGS__; }                \
+    } while (0)
+
+inline bool dim_ok(int d) { return d >= 4 && d <= 512 && (d % 4) == 0; }
+
+}  // namespace jmac

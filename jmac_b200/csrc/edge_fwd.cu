@@ -1,0 +1,217 @@
+// Edge phase of RelationAwareLayer.forward (comp_op='sub'), CSR-by-destination, one warp per work
+// item (a destination segment or a <=chunk slice of a hub segment).
+//
+// Reference being replaced: src/jmac_model.py:49,56-89 (message: gather x_i/x_j/rel, compose,
+// attention logit, message transform) + modules/helper/message_passing.py:4-29 (scatter_softmax,
+// division by edge_norm, weighted scatter-sum).  The E-row GEMMs of the reference are hoisted to
+// node level by the caller (P = X W_top, Q = X W_bot, S = R' W_bot); what is left per edge is two
+// gathered node rows (Q[j], X[j]), two cache-resident relation rows (S[t], R'[t]), a d-length dot,
+// an online segmented softmax and a weighted segmented sum: HBM-bound gather/reduce.
+//
+// Data layout: every table is fp32 row-major [rows, d]; a warp reads a row as VPL x float4 per lane
+// (512 B per load instruction, fully coalesced).  Algorithmic HBM bytes: 2*d*4 + 8 per edge,
+// 2*d*4 + 28 per destination.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace jmac {
+
+struct EdgeFwdParams {
+    const Item* items;
+    int n_items;
+    const int* csr_src;
+    const int* csr_type;
+    const float* sqrt_deg;
+    const float *P, *Q, *X, *S, *Rp, *a;
+    float slope;
+    int d4;
+    float* agg;
+    float* lse;
+    float* partial;  // [n_slots, d + 4]: (m, l, -, -) then the un-normalised weighted sum
+};
+
+template <int VPL>
+__device__ __forceinline__ float leaky_dot(const Row<VPL>& pi, const Row<VPL>& q, const Row<VPL>& s, const Row<VPL>& a, float slope) {
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        float4 z = pi.v[i] + q.v[i] - s.v[i];
+        z.x = z.x > 0.f ? z.x : slope * z.x;
+        z.y = z.y > 0.f ? z.y : slope * z.y;
+        z.z = z.z > 0.f ? z.z : slope * z.z;
+        z.w = z.w > 0.f ? z.w : slope * z.w;
+        part += dot4(a.v[i], z);
+    }
+    return part;
+}
+
+template <int VPL, int U>
+__global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int d4 = p.d4;
+    Row<VPL> av;
+    load_row<VPL, false>(av, p.a, 0, d4, lane);
+
+    for (int it = warp; it < p.n_items; it += nwarps) {
+        const Item item = p.items[it];
+        Row<VPL> pi;
+        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+        float m = -INFINITY, l = 0.f;
+        Row<VPL> acc;
+        acc.zero();
+        for (int base = item.beg; base < item.end; base += 32) {
+            const int cnt = min(32, item.end - base);
+            int jv = 0, tv = 0;
+            if (lane < cnt) {
+                jv = __ldg(p.csr_src + base + lane);
+                tv = __ldg(p.csr_type + base + lane);
+            }
+            int k = 0;
+            for (; k + U <= cnt; k += U) {
+                Row<VPL> q[U], x[U], s[U], r[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = __shfl_sync(FULL, jv, k + u);
+                    const int t = __shfl_sync(FULL, tv, k + u);
+                    load_row<VPL, true>(q[u], p.Q, j, d4, lane);
+                    load_row<VPL, true>(x[u], p.X, j, d4, lane);
+                    load_row<VPL, false>(s[u], p.S, t, d4, lane);
+                    load_row<VPL, false>(r[u], p.Rp, t, d4, lane);
+                }
+                float sc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) sc[u] = leaky_dot<VPL>(pi, q[u], s[u], av, p.slope);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(FULL, sc[u], o);
+                }
+                float mn = m;
+#pragma unroll
+                for (int u = 0; u < U; ++u) mn = fmaxf(mn, sc[u]);
+                const float corr = __expf(m - mn);
+                l *= corr;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) acc.v[i] = corr * acc.v[i];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float pe = __expf(sc[u] - mn);
+                    l += pe;
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) fma4(acc.v[i], pe, x[u].v[i] - r[u].v[i]);
+                }
+                m = mn;
+            }
+            for (; k < cnt; ++k) {
+                const int j = __shfl_sync(FULL, jv, k);
+                const int t = __shfl_sync(FULL, tv, k);
+                Row<VPL> q, x, s, r;
+                load_row<VPL, true>(q, p.Q, j, d4, lane);
+                load_row<VPL, true>(x, p.X, j, d4, lane);
+                load_row<VPL, false>(s, p.S, t, d4, lane);
+                load_row<VPL, false>(r, p.Rp, t, d4, lane);
+                const float sc = warp_sum(leaky_dot<VPL>(pi, q, s, av, p.slope));
+                const float mn = fmaxf(m, sc);
+                const float corr = __expf(m - mn);
+                const float pe = __expf(sc - mn);
+                l = l * corr + pe;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    acc.v[i] = corr * acc.v[i];
+                    fma4(acc.v[i], pe, x.v[i] - r.v[i]);
+                }
+                m = mn;
+            }
+        }
+        if (item.slot < 0) {
+            const float c = p.sqrt_deg[item.seg];
+            const float inv = l > 0.f ? c / l : 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
+            store_row<VPL>(acc, p.agg, item.seg, d4, lane);
+            if (lane == 0) p.lse[item.seg] = l > 0.f ? m + logf(l) : 0.f;
+        } else {
+            float* ps = p.partial + (size_t)item.slot * (size_t)(d4 * 4 + 4);
+            if (lane == 0) *reinterpret_cast<float4*>(ps) = make_float4(m, l, 0.f, 0.f);
+            store_row<VPL>(acc, ps + 4, 0, d4, lane);
+        }
+    }
+}
+
+// Two-level softmax merge for split (hub) destinations: one warp per split segment.
+template <int VPL>
+__global__ void __launch_bounds__(256) edge_fwd_merge_kernel(const Split* __restrict__ splits, int n_splits,
+                                                             const float* __restrict__ partial, const float* __restrict__ sqrt_deg,
+                                                             int d4, float* __restrict__ agg, float* __restrict__ lse) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_splits) return;
+    const Split sp = splits[w];
+    const size_t stride = (size_t)(d4 * 4 + 4);
+    const float* base = partial + (size_t)sp.first * stride;
+    float M = -INFINITY;
+    for (int k = lane; k < sp.count; k += 32) M = fmaxf(M, base[k * stride]);
+    M = warp_max(M);
+    float L = 0.f;
+    Row<VPL> acc;
+    acc.zero();
+    for (int k = 0; k < sp.count; ++k) {
+        const float4 ml = *reinterpret_cast<const float4*>(base + k * stride);
+        const float sc = ml.y > 0.f ? __expf(ml.x - M) : 0.f;
+        L += sc * ml.y;
+        Row<VPL> part;
+        load_row<VPL, true>(part, base + k * stride + 4, 0, d4, lane);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) fma4(acc.v[i], sc, part.v[i]);
+    }
+    const float inv = L > 0.f ? sqrt_deg[sp.seg] / L : 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
+    store_row<VPL>(acc, agg, sp.seg, d4, lane);
+    if (lane == 0) lse[sp.seg] = L > 0.f ? M + logf(L) : 0.f;
+}
+
+}  // namespace jmac
+
+using namespace jmac;
+
+extern "C" int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S, const float* Rp,
+                             const float* a_att, float leaky_slope, int d, float* agg, float* lse, void* stream) {
+    JMAC_ARG(plan && P && Q && X && S && Rp && a_att && agg && lse);
+    JMAC_ARG(dim_ok(d));
+    cudaStream_t st = (cudaStream_t)stream;
+    EdgeFwdParams p;
+    p.items = plan->dst_items.items;
+    p.n_items = plan->dst_items.n_items;
+    p.csr_src = plan->csr_src;
+    p.csr_type = plan->csr_type;
+    p.sqrt_deg = plan->sqrt_deg;
+    p.P = P; p.Q = Q; p.X = X; p.S = S; p.Rp = Rp; p.a = a_att;
+    p.slope = leaky_slope;
+    p.d4 = d / 4;
+    p.agg = agg; p.lse = lse;
+    p.partial = nullptr;
+    if (plan->dst_items.n_slots > 0) {
+        int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)(d + 4), &p.partial);
+        if (rc) return rc;
+    }
+    if (p.n_items == 0) return 0;
+    const int threads = 256;
+    JMAC_DISPATCH_VPL(d, {
+        constexpr int U = VPL == 1 ? 4 : 2;
+        auto kern = edge_fwd_kernel<VPL, U>;
+        int blocks = persistent_blocks(kern, threads, p.n_items);
+        kern<<<blocks, threads, 0, st>>>(p);
+        JMAC_LAUNCH_CHECK();
+        if (plan->dst_items.n_splits > 0) {
+            int mb = (plan->dst_items.n_splits * 32 + threads - 1) / threads;
+            edge_fwd_merge_kernel<VPL><<<mb, threads, 0, st>>>(plan->dst_items.splits, plan->dst_items.n_splits, p.partial,
+                                                                plan->sqrt_deg, p.d4, agg, lse);
+            JMAC_LAUNCH_CHECK();
+        }
+    });
+    return 0;
+}

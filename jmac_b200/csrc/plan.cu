@@ -1,0 +1,333 @@
+// Graph plan: COO (int64, as the reference passes it) -> three device-resident edge orderings.
+//   by destination (CSR, secondary key = relation type)  -> forward + backward dst pass
+//   by source                                            -> backward src pass (atomics-free dX, dQ)
+//   by relation type                                     -> backward relation pass
+// plus the work-item lists that split long segments (hubs) into warp-sized chunks.
+// Replaces RelationAwareLayer.compute_norm (src/jmac_model.py:99-109) and the index work of
+// MessagePassing.propagate (modules/helper/message_passing.py:69-81).
+#include <stdarg.h>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace jmac {
+
+static thread_local char g_err[768] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
+int plan_scratch(jmac_plan* p, size_t bytes, float** out) {
+    if (bytes > p->scratch_bytes) {
+        if (p->scratch) JMAC_CUDA(cudaFree(p->scratch));
+        p->scratch = nullptr;
+        p->scratch_bytes = 0;
+        JMAC_CUDA(cudaMalloc(&p->scratch, bytes));
+        p->scratch_bytes = bytes;
+    }
+    *out = p->scratch;
+    return 0;
+}
+
+static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
+    int b = 1;
+    while ((int64_t(1) << b) < n) ++b;
+    return b;
+}
+
+__global__ void make_keys_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                 const int64_t* __restrict__ typ, int64_t E, int64_t N, int64_t n_rel, int tb,
+                                 uint64_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bad) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int64_t r = row[e], c = col[e], t = typ[e];
+    if (r < 0 || r >= N || c < 0 || c >= N || t < 0 || t >= n_rel) {
+        atomicOr(bad, 1);
+        r = 0; t = 0;
+    }
+    keys[e] = ((uint64_t)r << tb) | (uint64_t)t;
+    vals[e] = (int)e;
+}
+
+__global__ void fill_csr_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ eid,
+                                const int64_t* __restrict__ col, int64_t E, int tb, int* __restrict__ csr_src,
+                                int* __restrict__ csr_type, int* __restrict__ csr_dst) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    uint64_t k = keys[p];
+    csr_dst[p] = (int)(k >> tb);
+    csr_type[p] = (int)(k & ((uint64_t(1) << tb) - 1));
+    csr_src[p] = (int)col[eid[p]];
+}
+
+// ptr[s] = first position whose (sorted) key is >= s, for s in [0, nseg]; ptr[nseg] = E.
+__global__ void build_ptr_kernel(const int* __restrict__ keys, int64_t E, int nseg, int* __restrict__ ptr) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p > E) return;
+    int prev = (p == 0) ? -1 : keys[p - 1];
+    int cur = (p == E) ? nseg : keys[p];
+    for (int s = prev + 1; s <= cur; ++s) ptr[s] = (int)p;
+}
+
+__global__ void iota_kernel(int* v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int)i;
+}
+
+__global__ void gather_int_kernel(const int* __restrict__ src, const int* __restrict__ idx, int64_t n, int* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+__global__ void sqrt_deg_kernel(const int* __restrict__ rowptr, int64_t N, float* __restrict__ out, int* __restrict__ max_deg) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int deg = rowptr[i + 1] - rowptr[i];
+    out[i] = sqrtf((float)deg);
+    int m = deg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_deg, m);
+}
+
+__global__ void item_counts_kernel(const int* __restrict__ ptr, int nseg, int chunk, int keep_empty,
+                                   int* __restrict__ n_it, int* __restrict__ n_sl, int* __restrict__ n_sp) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    int len = ptr[s + 1] - ptr[s];
+    int k = len == 0 ? keep_empty : (len + chunk - 1) / chunk;
+    n_it[s] = k;
+    n_sl[s] = k > 1 ? k : 0;
+    n_sp[s] = k > 1 ? 1 : 0;
+}
+
+__global__ void item_fill_kernel(const int* __restrict__ ptr, int nseg, int chunk, const int* __restrict__ n_it,
+                                 const int* __restrict__ off_it, const int* __restrict__ off_sl,
+                                 const int* __restrict__ off_sp, Item* __restrict__ items, Split* __restrict__ splits) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    int k = n_it[s];
+    if (k == 0) return;
+    int beg = ptr[s], end = ptr[s + 1];
+    int o = off_it[s];
+    if (k == 1) {
+        items[o] = Item{s, beg, end, -1};
+        return;
+    }
+    int so = off_sl[s];
+    for (int i = 0; i < k; ++i) {
+        int b = beg + i * chunk;
+        items[o + i] = Item{s, b, min(end, b + chunk), so + i};
+    }
+    splits[off_sp[s]] = Split{s, so, k, 0};
+}
+
+static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cudaStream_t st, ItemList* out) {
+    int *n_it = nullptr, *n_sl = nullptr, *n_sp = nullptr, *o_it = nullptr, *o_sl = nullptr, *o_sp = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    size_t nb = sizeof(int) * (size_t)(nseg + 1);
+    JMAC_CUDA(cudaMalloc(&n_it, nb)); JMAC_CUDA(cudaMalloc(&n_sl, nb)); JMAC_CUDA(cudaMalloc(&n_sp, nb));
+    JMAC_CUDA(cudaMalloc(&o_it, nb)); JMAC_CUDA(cudaMalloc(&o_sl, nb)); JMAC_CUDA(cudaMalloc(&o_sp, nb));
+    JMAC_CUDA(cudaMemsetAsync(n_it, 0, nb, st)); JMAC_CUDA(cudaMemsetAsync(n_sl, 0, nb, st)); JMAC_CUDA(cudaMemsetAsync(n_sp, 0, nb, st));
+    int threads = 256, blocks = (nseg + threads - 1) / threads;
+    if (nseg > 0) {
+        item_counts_kernel<<<blocks, threads, 0, st>>>(ptr, nseg, chunk, keep_empty, n_it, n_sl, n_sp);
+        JMAC_LAUNCH_CHECK();
+    }
+    // exclusive scans over nseg+1 entries (last entry of the counts is 0) -> totals land at [nseg]
+    JMAC_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, n_it, o_it, nseg + 1, st));
+    JMAC_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_it, o_it, nseg + 1, st));
+    JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_sl, o_sl, nseg + 1, st));
+    JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_sp, o_sp, nseg + 1, st));
+    int tot[3] = {0, 0, 0};
+    JMAC_CUDA(cudaMemcpyAsync(&tot[0], o_it + nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+    JMAC_CUDA(cudaMemcpyAsync(&tot[1], o_sl + nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+    JMAC_CUDA(cudaMemcpyAsync(&tot[2], o_sp + nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+    JMAC_CUDA(cudaStreamSynchronize(st));
+    out->n_items = tot[0]; out->n_slots = tot[1]; out->n_splits = tot[2];
+    JMAC_CUDA(cudaMalloc(&out->items, sizeof(Item) * (size_t)(tot[0] > 0 ? tot[0] : 1)));
+    JMAC_CUDA(cudaMalloc(&out->splits, sizeof(Split) * (size_t)(tot[2] > 0 ? tot[2] : 1)));
+    if (nseg > 0) {
+        item_fill_kernel<<<blocks, threads, 0, st>>>(ptr, nseg, chunk, n_it, o_it, o_sl, o_sp, out->items, out->splits);
+        JMAC_LAUNCH_CHECK();
+    }
+    JMAC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(n_it); cudaFree(n_sl); cudaFree(n_sp); cudaFree(o_it); cudaFree(o_sl); cudaFree(o_sp); cudaFree(tmp);
+    return 0;
+}
+
+static int sort_by_int_key(const int* keys_in, int64_t E, int end_bit, cudaStream_t st, int* keys_out, int* pos_out) {
+    int* iota = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    JMAC_CUDA(cudaMalloc(&iota, sizeof(int) * (size_t)(E > 0 ? E : 1)));
+    int threads = 256;
+    int64_t blocks = (E + threads - 1) / threads;
+    if (E > 0) { iota_kernel<<<(unsigned)blocks, threads, 0, st>>>(iota, E); JMAC_LAUNCH_CHECK(); }
+    JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned*)keys_in, (unsigned*)keys_out, iota, pos_out, (int)E, 0, end_bit, st));
+    JMAC_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+    JMAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned*)keys_in, (unsigned*)keys_out, iota, pos_out, (int)E, 0, end_bit, st));
+    JMAC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(iota); cudaFree(tmp);
+    return 0;
+}
+
+}  // namespace jmac
+
+using namespace jmac;
+
+extern "C" const char* jmac_version(void) { return "jmac_b200 0.1 (sm_100a)"; }
+extern "C" const char* jmac_last_error(void) { return jmac::g_err; }
+extern "C" uint64_t jmac_launch_count(void) { return __atomic_load_n(&jmac::g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int jmac_plan_destroy(jmac_plan* p) {
+    if (!p) return 0;
+    cudaFree(p->rowptr); cudaFree(p->csr_src); cudaFree(p->csr_type); cudaFree(p->csr_eid); cudaFree(p->csr_dst);
+    cudaFree(p->sqrt_deg); cudaFree(p->colptr); cudaFree(p->csc_pos); cudaFree(p->csc_dst);
+    cudaFree(p->typptr); cudaFree(p->typ_pos); cudaFree(p->typ_dst);
+    cudaFree(p->dst_items.items); cudaFree(p->dst_items.splits);
+    cudaFree(p->src_items.items); cudaFree(p->src_items.splits);
+    cudaFree(p->typ_items.items); cudaFree(p->typ_items.splits);
+    cudaFree(p->scratch);
+    delete p;
+    return 0;
+}
+
+static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, cudaStream_t st) {
+    const int64_t E = p->E, N = p->N, R = p->n_rel;
+    const size_t Eb = (size_t)(E > 0 ? E : 1);
+    const int tb = bits_for(R), nbits = bits_for(N);
+    JMAC_CUDA(cudaMalloc(&p->rowptr, sizeof(int) * (size_t)(N + 1)));
+    JMAC_CUDA(cudaMalloc(&p->colptr, sizeof(int) * (size_t)(N + 1)));
+    JMAC_CUDA(cudaMalloc(&p->typptr, sizeof(int) * (size_t)(R + 1)));
+    JMAC_CUDA(cudaMalloc(&p->sqrt_deg, sizeof(float) * (size_t)(N > 0 ? N : 1)));
+    JMAC_CUDA(cudaMalloc(&p->csr_src, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csr_type, sizeof(int) * Eb));
+    JMAC_CUDA(cudaMalloc(&p->csr_eid, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csr_dst, sizeof(int) * Eb));
+    JMAC_CUDA(cudaMalloc(&p->csc_pos, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csc_dst, sizeof(int) * Eb));
+    JMAC_CUDA(cudaMalloc(&p->typ_pos, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->typ_dst, sizeof(int) * Eb));
+
+    const int threads = 256;
+    const unsigned eblocks = (unsigned)((E + threads - 1) / threads);
+    const unsigned e1blocks = (unsigned)((E + 1 + threads - 1) / threads);
+    int* flags = nullptr;  // [0] = bad index flag, [1] = max degree
+    JMAC_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
+    JMAC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+
+    // ---- by destination, secondary key relation type
+    {
+        uint64_t *k_in = nullptr, *k_out = nullptr;
+        int* v_in = nullptr;
+        void* tmp = nullptr;
+        size_t tmp_bytes = 0;
+        JMAC_CUDA(cudaMalloc(&k_in, sizeof(uint64_t) * Eb)); JMAC_CUDA(cudaMalloc(&k_out, sizeof(uint64_t) * Eb));
+        JMAC_CUDA(cudaMalloc(&v_in, sizeof(int) * Eb));
+        if (E > 0) {
+            make_keys_kernel<<<eblocks, threads, 0, st>>>(d_row, d_col, d_type, E, N, R, tb, k_in, v_in, flags);
+            JMAC_LAUNCH_CHECK();
+        }
+        JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
+        JMAC_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+        JMAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
+        if (E > 0) {
+            fill_csr_kernel<<<eblocks, threads, 0, st>>>(k_out, p->csr_eid, d_col, E, tb, p->csr_src, p->csr_type, p->csr_dst);
+            JMAC_LAUNCH_CHECK();
+        }
+        int bad = 0;
+        JMAC_CUDA(cudaMemcpyAsync(&bad, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        JMAC_CUDA(cudaStreamSynchronize(st));
+        cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(tmp);
+        if (bad) {
+            cudaFree(flags);
+            set_error("jmac_plan_create: edge_index / edge_type entry out of range (N=%lld, n_rel=%lld)", (long long)N, (long long)R);
+            return JMAC_ERANGE;
+        }
+    }
+    build_ptr_kernel<<<e1blocks, threads, 0, st>>>(p->csr_dst, E, (int)N, p->rowptr);
+    JMAC_LAUNCH_CHECK();
+    if (N > 0) {
+        sqrt_deg_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(p->rowptr, N, p->sqrt_deg, flags + 1);
+        JMAC_LAUNCH_CHECK();
+    }
+    JMAC_CUDA(cudaMemcpyAsync(&p->max_deg, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+
+    // ---- by source (stable: positions stay in destination order inside a source segment)
+    {
+        int* sorted = nullptr;
+        JMAC_CUDA(cudaMalloc(&sorted, sizeof(int) * Eb));
+        int rc = sort_by_int_key(p->csr_src, E, nbits, st, sorted, p->csc_pos);
+        if (rc) return rc;
+        build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)N, p->colptr);
+        JMAC_LAUNCH_CHECK();
+        if (E > 0) { gather_int_kernel<<<eblocks, threads, 0, st>>>(p->csr_dst, p->csc_pos, E, p->csc_dst); JMAC_LAUNCH_CHECK(); }
+        // ---- by relation type
+        rc = sort_by_int_key(p->csr_type, E, tb, st, sorted, p->typ_pos);
+        if (rc) return rc;
+        build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)R, p->typptr);
+        JMAC_LAUNCH_CHECK();
+        if (E > 0) { gather_int_kernel<<<eblocks, threads, 0, st>>>(p->csr_dst, p->typ_pos, E, p->typ_dst); JMAC_LAUNCH_CHECK(); }
+        JMAC_CUDA(cudaStreamSynchronize(st));
+        cudaFree(sorted);
+    }
+    cudaFree(flags);
+    int rc = build_items(p->rowptr, (int)N, p->chunk, 1, st, &p->dst_items);
+    if (rc) return rc;
+    rc = build_items(p->colptr, (int)N, p->chunk, 1, st, &p->src_items);
+    if (rc) return rc;
+    // relation pass: larger chunks (one CTA-wide warp loop per item), empty relations skipped
+    rc = build_items(p->typptr, (int)R, p->chunk, 0, st, &p->typ_items);
+    return rc;
+}
+
+extern "C" int jmac_plan_create(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, int64_t E, int64_t N,
+                                int64_t n_rel, int chunk, void* stream, jmac_plan** out) {
+    JMAC_ARG(out != nullptr);
+    *out = nullptr;
+    JMAC_ARG(E >= 0 && E < (int64_t(1) << 31) - 1);
+    JMAC_ARG(N > 0 && N < (int64_t(1) << 31) - 1);
+    JMAC_ARG(n_rel > 0 && n_rel < (int64_t(1) << 24));
+    JMAC_ARG(E == 0 || (d_row && d_col && d_type));
+    JMAC_ARG(chunk >= 0 && chunk <= (1 << 20));
+    jmac_plan* p = new (std::nothrow) jmac_plan();
+    if (!p) return JMAC_ENOMEM;
+    p->E = E; p->N = N; p->n_rel = n_rel;
+    p->chunk = chunk > 0 ? chunk : 256;
+    int rc = plan_build(p, d_row, d_col, d_type, (cudaStream_t)stream);
+    if (rc) { jmac_plan_destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+extern "C" int jmac_plan_info(const jmac_plan* p, int64_t info[8]) {
+    JMAC_ARG(p && info);
+    info[0] = p->E; info[1] = p->N; info[2] = p->n_rel; info[3] = p->chunk;
+    info[4] = p->dst_items.n_items; info[5] = p->src_items.n_items; info[6] = p->typ_items.n_items; info[7] = p->max_deg;
+    return 0;
+}
+
+extern "C" int jmac_plan_export(const jmac_plan* p, int32_t* rowptr, int32_t* csr_src, int32_t* csr_type, int32_t* csr_eid,
+                                float* sqrt_deg, void* stream) {
+    JMAC_ARG(p != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rowptr) JMAC_CUDA(cudaMemcpyAsync(rowptr, p->rowptr, sizeof(int) * (size_t)(p->N + 1), cudaMemcpyDeviceToDevice, st));
+    if (csr_src && p->E) JMAC_CUDA(cudaMemcpyAsync(csr_src, p->csr_src, sizeof(int) * (size_t)p->E, cudaMemcpyDeviceToDevice, st));
+    if (csr_type && p->E) JMAC_CUDA(cudaMemcpyAsync(csr_type, p->csr_type, sizeof(int) * (size_t)p->E, cudaMemcpyDeviceToDevice, st));
+    if (csr_eid && p->E) JMAC_CUDA(cudaMemcpyAsync(csr_eid, p->csr_eid, sizeof(int) * (size_t)p->E, cudaMemcpyDeviceToDevice, st));
+    if (sqrt_deg) JMAC_CUDA(cudaMemcpyAsync(sqrt_deg, p->sqrt_deg, sizeof(float) * (size_t)p->N, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

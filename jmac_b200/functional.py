@@ -1,0 +1,372 @@
+"""Host-side glue between PyTorch tensors and the C ABI: the graph-plan cache and the
+``torch.autograd.Function`` wrappers around the sm_100a kernels.  PyTorch is plumbing here (device
+memory, streams, autograd bookkeeping, the node-level library GEMMs); every per-edge / per-triple
+operation runs in libjmac_b200.so.  No CPU fallback: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.JmacError("jmac_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def as_index(x, device) -> torch.Tensor:
+    """Normalise the index types the reference passes around (python lists, numpy int64, numpy
+    float64 such as ``1951.0`` from train.py:189-192, LongTensors) to a contiguous int64 device
+    tensor, once, at the boundary (SURVEY 8c 'input-type quirks')."""
+    if torch.is_tensor(x):
+        t = x
+    else:
+        a = np.asarray(x)
+        if a.dtype.kind == "f":
+            a = a.astype(np.int64)
+        t = torch.from_numpy(np.ascontiguousarray(a.astype(np.int64, copy=False)))
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# graph plan
+# ----------------------------------------------------------------------------------------------
+class GraphPlan:
+    """Owns a ``jmac_plan`` (CSR-by-destination + by-source + by-relation orderings)."""
+
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int, chunk: int = 0):
+        _need_cuda(edge_index, edge_type)
+        lib = _lib.load()
+        ei = edge_index.to(torch.int64).contiguous()
+        et = edge_type.to(torch.int64).contiguous()
+        if ei.dim() != 2 or ei.shape[0] != 2 or et.shape[0] != ei.shape[1]:
+            raise ValueError("edge_index must be [2,E] and edge_type [E]")
+        self.E, self.N, self.n_rel = int(ei.shape[1]), int(num_ent), int(n_rel)
+        self.device = ei.device
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.jmac_plan_create(ptr(ei[0]), ptr(ei[1]), ptr(et), self.E, self.N, self.n_rel, int(chunk), stream_ptr(),
+                                       ctypes.byref(handle)), "jmac_plan_create")
+        self._h = handle
+        info = (ctypes.c_int64 * 8)()
+        check(lib.jmac_plan_info(self._h, info), "jmac_plan_info")
+        self.info = list(info)
+        self.max_in_degree = int(info[7])
+
+    @property
+    def handle(self):
+        return self._h
+
+    def export(self):
+        """(rowptr, csr_src, csr_type, csr_eid, sqrt_deg) as device tensors -- for tests."""
+        lib = _lib.load()
+        rowptr = torch.empty(self.N + 1, dtype=torch.int32, device=self.device)
+        src = torch.empty(self.E, dtype=torch.int32, device=self.device)
+        typ = torch.empty(self.E, dtype=torch.int32, device=self.device)
+        eid = torch.empty(self.E, dtype=torch.int32, device=self.device)
+        sdeg = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.jmac_plan_export(self._h, ptr(rowptr), ptr(src), ptr(typ), ptr(eid), ptr(sdeg), stream_ptr()), "jmac_plan_export")
+        return rowptr, src, typ, eid, sdeg
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().jmac_plan_destroy(h)
+            except Exception:
+                pass
+
+
+_PLAN_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_PLAN_CACHE_SIZE = 16
+
+
+def get_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int) -> GraphPlan:
+    """Plan cache keyed on tensor identity + version: the reference reuses one edge set for
+    thousands of optimiser steps (train.py:447-485) and rebuilds tensors when the graph changes."""
+    key = (edge_index.data_ptr(), edge_type.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_type._version,
+           int(num_ent), int(n_rel), str(edge_index.device))
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return hit[0]
+    plan = GraphPlan(edge_index, edge_type, num_ent, n_rel)
+    # keep the key tensors alive so that their addresses cannot be recycled while cached
+    _PLAN_CACHE[key] = (plan, edge_index, edge_type)
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+# edge phase
+# ----------------------------------------------------------------------------------------------
+class EdgePhaseFn(torch.autograd.Function):
+    """agg[i] = sqrt(deg_i) * sum_e softmax_i(a . lrelu(P[i]+Q[j]-S[t])) * (X[j] - Rp[t])."""
+
+    @staticmethod
+    def forward(ctx, plan: GraphPlan, P, Q, X, S, Rp, a_att, slope: float):
+        _need_cuda(P, Q, X, S, Rp, a_att)
+        lib = _lib.load()
+        P, Q, X, S, Rp, a = (_f32c(t) for t in (P, Q, X, S, Rp, a_att.reshape(-1)))
+        N, d = X.shape
+        if N != plan.N or S.shape[0] != plan.n_rel or Rp.shape[0] != plan.n_rel:
+            raise ValueError("table sizes do not match the graph plan")
+        agg = torch.empty_like(X)
+        lse = torch.empty(N, dtype=torch.float32, device=X.device)
+        with torch.cuda.device(X.device):
+            check(lib.jmac_edge_fwd(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
+                                    stream_ptr()), "jmac_edge_fwd")
+        ctx.plan, ctx.slope = plan, float(slope)
+        ctx.save_for_backward(P, Q, X, S, Rp, a, agg, lse)
+        ctx.a_shape = a_att.shape
+        return agg
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        P, Q, X, S, Rp, a, agg, lse = ctx.saved_tensors
+        plan, slope = ctx.plan, ctx.slope
+        N, d = X.shape
+        G = _f32c(g)
+        dev = X.device
+        dP = torch.empty_like(X)
+        dXe = torch.empty_like(X)
+        dQ = torch.empty_like(X)
+        dRp = torch.empty_like(Rp)
+        dS = torch.empty_like(S)
+        da = torch.zeros(d, dtype=torch.float32, device=dev)
+        rec_bytes = int(lib.jmac_edge_record_bytes(d))
+        erec = torch.empty(max(plan.E, 1) * rec_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr()
+            check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G),
+                                        ptr(dP), ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
+            check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(dXe), ptr(dQ), st), "jmac_edge_bwd_src")
+            check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(dRp), ptr(dS), st), "jmac_edge_bwd_rel")
+        return None, dP, dQ, dXe, dS, dRp, da.view(ctx.a_shape), None
+
+
+def edge_phase(plan, P, Q, X, S, Rp, a_att, slope):
+    return EdgePhaseFn.apply(plan, P, Q, X, S, Rp, a_att, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# BatchNorm1d(over nodes) + tanh
+# ----------------------------------------------------------------------------------------------
+class BNTanhFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pre, gamma, beta, running_mean, running_var, momentum, eps, training, group):
+        _need_cuda(pre, gamma, beta)
+        lib = _lib.load()
+        pre, gamma, beta = _f32c(pre), _f32c(gamma), _f32c(beta)
+        N, d = pre.shape
+        dev = pre.device
+        out = torch.empty_like(pre)
+        mean = torch.empty(d, dtype=torch.float32, device=dev)
+        rstd = torch.empty(d, dtype=torch.float32, device=dev)
+        n_total = N
+        sums = None
+        with torch.cuda.device(dev):
+            st = stream_ptr()
+            if training:
+                sums = torch.zeros(2 * d + 1, dtype=torch.float64, device=dev)
+                check(lib.jmac_bn_stats(ptr(pre), N, d, ptr(sums), st), "jmac_bn_stats")
+                if group is not None:  # BN is over ALL nodes: all-reduce (sum x, sum x^2, n) across destination shards
+                    sums[2 * d] = float(N)
+                    torch.distributed.all_reduce(sums, group=group)
+                    n_total = int(round(float(sums[2 * d].item())))
+                st = stream_ptr()
+            check(lib.jmac_bn_tanh_apply(ptr(pre), N, d, ptr(sums), n_total, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                         float(momentum), float(eps), int(bool(training)), ptr(out), ptr(mean), ptr(rstd), st),
+                  "jmac_bn_tanh_apply")
+        ctx.save_for_backward(pre, out, gamma, mean, rstd)
+        ctx.training, ctx.n_total, ctx.group = bool(training), n_total, group
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        pre, out, gamma, mean, rstd = ctx.saved_tensors
+        N, d = pre.shape
+        dev = pre.device
+        gout = _f32c(gout)
+        bsums = torch.zeros(2 * d, dtype=torch.float64, device=dev)
+        gpre = torch.empty_like(pre)
+        dgamma = torch.empty(d, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(d, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr()
+            check(lib.jmac_bn_tanh_bwd_stats(ptr(gout), ptr(out), ptr(pre), N, d, ptr(mean), ptr(rstd), ptr(bsums), st), "jmac_bn_tanh_bwd_stats")
+            if ctx.group is not None and ctx.training:
+                # the per-shard (sum dy, sum dy*xhat) are also the shard's contribution to dbeta/dgamma;
+                # the statistics coupling needs the global sums, the parameter grads are all-reduced by the caller
+                local = bsums.clone()
+                torch.distributed.all_reduce(bsums, group=ctx.group)
+            else:
+                local = bsums
+            check(lib.jmac_bn_tanh_bwd_apply(ptr(gout), ptr(out), ptr(pre), N, d, ptr(mean), ptr(rstd), ptr(gamma), ptr(bsums),
+                                             ctx.n_total, int(ctx.training), ptr(gpre), None, None, st), "jmac_bn_tanh_bwd_apply")
+        dbeta = local[:d].to(torch.float32)
+        dgamma = local[d:].to(torch.float32)
+        return gpre, dgamma, dbeta, None, None, None, None, None, None
+
+
+def bn_tanh(pre, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, training=True, group=None):
+    return BNTanhFn.apply(pre, gamma, beta, running_mean, running_var, momentum, eps, training, group)
+
+
+# ----------------------------------------------------------------------------------------------
+# completion scorer
+# ----------------------------------------------------------------------------------------------
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class TransEMarginFn(torch.autograd.Function):
+    """loss[l] of include/jmac_b200.h:jmac_transe_margin_fwd for n_layers (ent, rel) table pairs."""
+
+    @staticmethod
+    def forward(ctx, h, r, t, batch_size: int, margin: float, *tables):
+        lib = _lib.load()
+        n_layers = len(tables) // 2
+        ents = [_f32c(x) for x in tables[:n_layers]]
+        rels = [_f32c(x) for x in tables[n_layers:]]
+        _need_cuda(*ents, *rels)
+        dev = ents[0].device
+        d = ents[0].shape[1]
+        h, r, t = as_index(h, dev), as_index(r, dev), as_index(t, dev)
+        M = int(h.numel())
+        if int(r.numel()) != M or int(t.numel()) != M:
+            raise RuntimeError("batch_h, batch_r, batch_t must have the same length")
+        B = min(int(batch_size), M)
+        if M % B != 0 or M // B < 2:
+            # same failure the reference hits in score.view(-1, batch_size) (src/jmac_model.py:358,367)
+            raise RuntimeError(f"shape '[-1, {B}]' is invalid for input of size {M - B}")
+        score = torch.empty(n_layers * M, dtype=torch.float32, device=dev)
+        loss = torch.empty(n_layers, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.jmac_transe_margin_fwd(_ptr_array(ents), _ptr_array(rels), n_layers, d, ptr(h), ptr(r), ptr(t), M, B,
+                                             ents[0].shape[0], rels[0].shape[0], float(margin), ptr(score), ptr(loss), stream_ptr()),
+                  "jmac_transe_margin_fwd")
+        ctx.save_for_backward(h, r, t, score, *ents, *rels)
+        ctx.meta = (n_layers, d, M, B, float(margin))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        lib = _lib.load()
+        n_layers, d, M, B, margin = ctx.meta
+        h, r, t, score = ctx.saved_tensors[:4]
+        ents = list(ctx.saved_tensors[4:4 + n_layers])
+        rels = list(ctx.saved_tensors[4 + n_layers:])
+        dev = ents[0].device
+        gloss = _f32c(gloss)
+        d_ents = [torch.zeros_like(x) for x in ents]
+        d_rels = [torch.zeros_like(x) for x in rels]
+        with torch.cuda.device(dev):
+            check(lib.jmac_transe_margin_bwd(_ptr_array(ents), _ptr_array(rels), n_layers, d, ptr(h), ptr(r), ptr(t), M, B, margin,
+                                             ptr(score), ptr(gloss), _ptr_array(d_ents), _ptr_array(d_rels), stream_ptr()),
+                  "jmac_transe_margin_bwd")
+        return (None, None, None, None, None, *d_ents, *d_rels)
+
+
+def transe_margin_loss(ents: List[torch.Tensor], rels: List[torch.Tensor], h, r, t, batch_size: int, margin: float) -> torch.Tensor:
+    """Per-layer losses [n_layers] (sum them as src/jmac_model.py:378 does)."""
+    return TransEMarginFn.apply(h, r, t, batch_size, margin, *ents, *rels)
+
+
+class PairCosFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B, ia, ib):
+        lib = _lib.load()
+        A, B = _f32c(A), _f32c(B)
+        _need_cuda(A, B)
+        dev = A.device
+        ia, ib = as_index(ia, dev).reshape(-1), as_index(ib, dev).reshape(-1)
+        M = int(ia.numel())
+        cosv = torch.empty(M, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.jmac_pair_cos_fwd(ptr(A), ptr(B), A.shape[1], ptr(ia), ptr(ib), M, ptr(cosv), stream_ptr()), "jmac_pair_cos_fwd")
+        ctx.save_for_backward(A, B, ia, ib)
+        return cosv
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        A, B, ia, ib = ctx.saved_tensors
+        g = _f32c(g)
+        dA = torch.zeros_like(A)
+        dB = torch.zeros_like(B)
+        with torch.cuda.device(A.device):
+            check(lib.jmac_pair_cos_bwd(ptr(A), ptr(B), A.shape[1], ptr(ia), ptr(ib), int(ia.numel()), ptr(g), ptr(dA), ptr(dB), stream_ptr()),
+                  "jmac_pair_cos_bwd")
+        return dA, dB, None, None
+
+
+def pair_cos(A, B, ia, ib) -> torch.Tensor:
+    return PairCosFn.apply(A, B, ia, ib)
+
+
+# ----------------------------------------------------------------------------------------------
+# link prediction
+# ----------------------------------------------------------------------------------------------
+def l1_dist(ents, rels, e_idx, r_idx, pred_head=False) -> torch.Tensor:
+    lib = _lib.load()
+    ents = [_f32c(x.detach()) for x in ents]
+    rels = [_f32c(x.detach()) for x in rels]
+    _need_cuda(*ents, *rels)
+    dev = ents[0].device
+    e_idx, r_idx = as_index(e_idx, dev), as_index(r_idx, dev)
+    Bq, N, d = int(e_idx.numel()), ents[0].shape[0], ents[0].shape[1]
+    dist = torch.empty(Bq, N, dtype=torch.float32, device=dev)
+    if Bq == 0:
+        return dist
+    with torch.cuda.device(dev):
+        check(lib.jmac_l1_dist(_ptr_array(ents), _ptr_array(rels), len(ents), d, ptr(e_idx), ptr(r_idx), Bq, N, int(pred_head), ptr(dist),
+                               stream_ptr()), "jmac_l1_dist")
+    return dist
+
+
+def l1_rank(ents, rels, e_idx, r_idx, t_idx, filt_ptr=None, filt_idx=None, pred_head=False) -> torch.Tensor:
+    """1-based (filtered) rank of each target by counting; int32 [B]."""
+    lib = _lib.load()
+    ents = [_f32c(x.detach()) for x in ents]
+    rels = [_f32c(x.detach()) for x in rels]
+    _need_cuda(*ents, *rels)
+    dev = ents[0].device
+    e_idx, r_idx, t_idx = as_index(e_idx, dev), as_index(r_idx, dev), as_index(t_idx, dev)
+    Bq, N, d = int(e_idx.numel()), ents[0].shape[0], ents[0].shape[1]
+    rank = torch.empty(Bq, dtype=torch.int32, device=dev)
+    if Bq == 0:
+        return rank
+    if filt_ptr is not None:
+        filt_ptr, filt_idx = as_index(filt_ptr, dev), as_index(filt_idx, dev)
+    with torch.cuda.device(dev):
+        check(lib.jmac_l1_rank(_ptr_array(ents), _ptr_array(rels), len(ents), d, ptr(e_idx), ptr(r_idx), ptr(t_idx), Bq, N, int(pred_head),
+                               ptr(filt_ptr), ptr(filt_idx), ptr(rank), stream_ptr()), "jmac_l1_rank")
+    return rank

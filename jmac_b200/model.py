@@ -1,0 +1,254 @@
+"""Drop-in replacements for ``RelationAwareLayer`` and ``JMAC`` of the reference's
+``src/jmac_model.py`` -- same constructor arguments, parameter / ``state_dict`` names, method
+signatures, return values and error behaviour -- with the hot path running in hand-written sm_100a
+kernels (libjmac_b200.so) instead of un-fused eager ops.  Host code stays PyTorch.
+
+What runs where
+  * per-edge work (gathers, composition, attention logits, edge softmax, sqrt(deg) normalisation,
+    scatter-sum, and all of its backward), BatchNorm+tanh, the TransE-L1 margin scorer, the pair
+    cosine of the alignment losses and the L1 link-prediction distances: CUDA kernels;
+  * the node / relation-level dense products (X W_top, X W_bot, R' W_bot, (.) gcn_weight, the
+    relation MLPs): ``torch.mm`` (cuBLAS fp32, plain library GEMMs) with autograd.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.init import xavier_normal_
+
+from . import functional as JF
+
+
+def get_param(shape):
+    """modules/helper/helper.py:68-74 -- xavier_normal_ initialised Parameter."""
+    param = nn.Parameter(torch.empty(*shape))
+    xavier_normal_(param.data)
+    return param
+
+
+class RelationAwareLayer(nn.Module):
+    """src/jmac_model.py:10-109.  ``forward(ent_emb, rel_emb, edge_index, edge_type) -> [N, out]``.
+
+    The reference computes, per edge, ``cat(x_i, x_j - r_t) @ w_att`` and ``(x_j - r_t) @ gcn_weight``
+    (two E-row GEMMs).  Here both are hoisted to node level: with
+    ``w_att = [W_top; W_bot]``, ``P = X W_top``, ``Q = X W_bot``, ``S = R' W_bot`` the logit is
+    ``a . lrelu(P[i] + Q[j] - S[t])`` and the message GEMM is applied once after aggregation.
+    The self-loop ``propagate`` (:50) has a singleton softmax (== 1) and no norm, so it reduces to
+    ``(X - R'[loop]) @ gcn_weight``; attention parameters get no gradient from it, as in the reference.
+    """
+
+    def __init__(self, in_channels, out_channels, rel_dim, act=lambda x: x, args=None):
+        super().__init__()
+        if in_channels != out_channels:
+            raise NotImplementedError("the reference only instantiates square layers (src/jmac_model.py:147-149)")
+        self.layer_act = act
+        self.args = args
+        self.rel_transform_weight1 = get_param((rel_dim, in_channels))
+        self.rel_transform_weight2 = get_param((in_channels, in_channels))
+        self.gcn_weight = get_param((in_channels, out_channels))
+        self.loop_rel = get_param((1, rel_dim))
+        self.w_att = get_param((2 * in_channels, out_channels))
+        self.a_att = get_param((out_channels, 1))
+        self.leaky_slope = float(args.leaky_relu_w)
+        self.rel_act = getattr(args, "rel_act", "leaky")          # 'relu' = JMAC_DBPv1/models/jmac_model.py:27,51
+        self.bn = nn.BatchNorm1d(out_channels)
+        self.comp_op = args.comp_op
+        self.in_channels = in_channels
+        self.dist_group = None      # set by jmac_b200.dist for destination-sharded execution
+
+    def relation_transform(self, rel_emb):
+        rel = torch.cat([rel_emb, self.loop_rel], dim=0)                        # :39
+        rel = torch.mm(rel, self.rel_transform_weight1)                         # :40
+        rel = F.leaky_relu(rel, self.leaky_slope) if self.rel_act == "leaky" else F.relu(rel)   # :41
+        return torch.mm(rel, self.rel_transform_weight2)                        # :42
+
+    def forward(self, ent_emb, rel_emb, edge_index, edge_type):
+        if self.comp_op == "mult":
+            raise NotImplementedError("comp_op='mult' does not factor to node level; scheduled (DESIGN.md 'next')")
+        if self.comp_op != "sub":
+            raise NotImplementedError                                            # :65-66
+        if self.layer_act is not torch.tanh:
+            raise NotImplementedError("the fused BN+activation kernel implements tanh (BaseModel.act, src/jmac_model.py:118)")
+        num_ent = ent_emb.size(0)
+        d = self.in_channels
+        Rp = self.relation_transform(rel_emb)                                    # [nr+1, d]; row nr = self loop
+        plan = JF.get_plan(edge_index, edge_type, num_ent, Rp.size(0))
+        X = ent_emb.contiguous()
+        P = torch.mm(X, self.w_att[:d])
+        Q = torch.mm(X, self.w_att[d:])
+        S = torch.mm(Rp, self.w_att[d:])
+        agg = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope)   # neighbours, pre-GEMM
+        pre = torch.mm(agg + X - Rp[-1], self.gcn_weight * 0.5)                  # (neigh + self)/2, :49-52
+        training = self.training or not self.bn.track_running_stats
+        if self.training and self.bn.track_running_stats:
+            self.bn.num_batches_tracked += 1
+        momentum = self.bn.momentum if self.bn.momentum is not None else 0.1
+        return JF.bn_tanh(pre, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var, momentum, self.bn.eps,
+                          training, self.dist_group)
+
+
+class BaseModel(nn.Module):
+    """src/jmac_model.py:112-122."""
+
+    def __init__(self):
+        super().__init__()
+        self.act = torch.tanh
+        self.bceloss = nn.BCELoss()
+
+    def triple_loss(self, pred, true_label):
+        return self.bceloss(pred, true_label)
+
+
+class JMAC(BaseModel):
+    """src/jmac_model.py:125-380 -- same parameters (names, shapes, init order) and methods."""
+
+    def __init__(self, args, entity_name_emb, num_relations, num_entities):
+        super().__init__()
+        self.args = args
+        self.ent_info_att = torch.FloatTensor(entity_name_emb)
+        assert entity_name_emb.shape[0] == num_entities
+        self.entity_dim = args.dim
+        self.relation_dim = args.dim
+        self.device = args.device
+        d = self.entity_dim
+        self.ent_init_att_completion = get_param((num_entities, d))
+        self.rel_init_att_completion = get_param((num_relations, d))
+        self.rel_init_att_alignment = get_param((num_relations, d))
+
+        self.completion_dropout = nn.Dropout(args.dropout)
+        self.atv_mlp = nn.LeakyReLU(args.leaky_relu_w)
+        self.conv1_alignment = RelationAwareLayer(d, d, rel_dim=d, act=self.act, args=args)
+        self.conv2_alignment = RelationAwareLayer(d, d, rel_dim=d, act=self.act, args=args)
+        self.conv1_completion = RelationAwareLayer(d, d, rel_dim=d, act=self.act, args=args)
+
+        self.name_linear = get_param((self.ent_info_att.shape[1], d))
+        self.margin_align = args.margin_align
+        self.k = args.num_negative
+        self.margin_completion = nn.Parameter(torch.Tensor([args.margin_completion]))
+        self.margin_completion.requires_grad = False
+
+        L = args.num_gcn_layer
+        self.uni_linear1_1, self.uni_linear1_2 = get_param((d * L, d)), get_param((d, d))
+        self.uni_linear2_1, self.uni_linear2_2 = get_param((d * L, d)), get_param((d, d))
+        self.rel_linear11, self.rel_linear12 = get_param((d, d)), get_param((d, d))
+        self.rel_linear21, self.rel_linear22 = get_param((d, d)), get_param((d, d))
+        self.rel_linear11_uni, self.rel_linear12_uni = get_param((d, d)), get_param((d, d))
+        self.all_linear_completion = get_param((d * (L + 1), d))
+
+        self.forward_base = self.forward_no_name if self.args.no_name_info else self.forward_name
+        self._name_dev = None     # device-resident copy of ent_info_att (the reference re-uploads it every call, :177)
+
+    # ---- encoders -------------------------------------------------------------------------
+    def _name_table(self, device):
+        if self._name_dev is None or self._name_dev.device != torch.device(device):
+            self._name_dev = self.ent_info_att.to(device)
+        return self._name_dev
+
+    def forward_name(self, edge_index, edge_type, ent_bases, rel_bases):
+        """:172-204."""
+        lo, hi = ent_bases
+        rlo, rhi = rel_bases
+        dev = self.ent_init_att_completion.device
+        e0 = self.ent_init_att_completion[lo:hi]
+        name = torch.mm(self._name_table(dev)[lo:hi], self.name_linear)
+        e0n = self.completion_dropout(F.normalize(e0))
+        a0 = torch.mm(torch.cat((e0n, name), dim=1), self.uni_linear1_1)
+        a1 = self.conv1_alignment(a0, self.rel_init_att_alignment[rlo:rhi], edge_index, edge_type)
+        align_embs = [a0, a1]
+        comp_embs = [e0]
+        comp_rels = [self.rel_init_att_completion[rlo:rhi]]
+        if self.args.num_gcn_layer == 2:
+            c1 = self.conv1_completion(e0, self.rel_init_att_completion[rlo:rhi], edge_index, edge_type)
+            c1n = self.completion_dropout(F.normalize(c1))
+            a_in = torch.mm(torch.cat((c1n, a1), dim=1), self.uni_linear2_1)
+            r1 = torch.mm(self.atv_mlp(torch.mm(self.rel_init_att_completion[rlo:rhi], self.rel_linear11)), self.rel_linear12)
+            ar = torch.mm(self.atv_mlp(torch.mm(self.rel_init_att_alignment[rlo:rhi], self.rel_linear11_uni)), self.rel_linear12_uni)
+            a2 = self.conv2_alignment(a_in, ar, edge_index, edge_type)
+            align_embs.append(a2)
+            comp_embs.append(c1)
+            comp_rels.append(r1)
+        out = torch.mm(torch.cat(align_embs, dim=1), self.all_linear_completion)
+        return out, comp_embs, comp_rels
+
+    def forward_no_name(self, edge_index, edge_type, ent_bases, rel_bases):
+        """:207-220."""
+        e0 = self.ent_init_att_completion[ent_bases[0]:ent_bases[1]]
+        r0 = self.rel_init_att_completion[rel_bases[0]:rel_bases[1]]
+        comp_embs, comp_rels = [e0], [r0]
+        if self.args.num_gcn_layer == 2:
+            e1 = self.conv1_completion(e0, r0, edge_index, edge_type)
+            r1 = torch.mm(self.atv_mlp(torch.mm(r0, self.rel_linear11)), self.rel_linear12)
+            comp_embs.append(e1)
+            comp_rels.append(r1)
+        return comp_embs[-1], comp_embs, comp_rels
+
+    def get_emb(self, edge_index, edge_type, ent_bases, rel_bases, pyt=False):
+        """:223-234."""
+        a, comps, _ = self.forward_base(edge_index, edge_type, ent_bases, rel_bases)
+        a = F.normalize(a, 2, -1)
+        c = F.normalize(comps[-1], 2, -1)
+        if pyt:
+            return a.detach().cpu(), c.detach().cpu()
+        return a.detach().cpu().numpy(), c.detach().cpu().numpy()
+
+    # ---- losses ---------------------------------------------------------------------------
+    def alignment_loss_simple(self, links, ent_embeddings1, ent_embeddings2):
+        """:237-249 -- mean cosine distance of the seed links."""
+        if not len(links):
+            return 0
+        links = np.asarray(links) if not torch.is_tensor(links) else links
+        cosv = JF.pair_cos(ent_embeddings1, ent_embeddings2, links[:, 0].reshape(-1), links[:, 1].reshape(-1))
+        return (1 - cosv).mean()
+
+    def alignment_loss(self, feeddict, edge_index1, edge_type1, edge_index2, edge_type2):
+        """:252-292."""
+        links = feeddict["links"]
+        if not len(links):
+            return 0
+        e1, _, _ = self.forward_base(edge_index1, edge_type1, feeddict["ent_bases1"], feeddict["rel_bases1"])
+        e2, _, _ = self.forward_base(edge_index2, edge_type2, feeddict["ent_bases2"], feeddict["rel_bases2"])
+        links = np.asarray(links) if not torch.is_tensor(links) else links
+        n = len(links)
+        A = 1 - JF.pair_cos(e1, e2, links[:, 0].reshape(-1), links[:, 1].reshape(-1))
+        D = A + self.margin_align
+        total = 0
+        for left, right in (("neg_left", "neg_right"), ("neg2_left", "neg2_right")):
+            Bc = 1 - JF.pair_cos(e1, e2, feeddict[left], feeddict[right])
+            total = total + F.relu(-Bc.view(n, -1) + D.view(n, 1)).sum()
+        return total / (2 * self.k * n) * 1
+
+    def forward_linkpred(self, e_index, r_index, edge_index, edge_type, all_index, ent_bases, rel_bases, pred_head=False):
+        """:295-313.  ``all_index`` is ``list(range(N))`` at every call site (src/validate.py:44)."""
+        _, ents, rels = self.forward_base(edge_index, edge_type, ent_bases, rel_bases)
+        L = self.args.num_gcn_layer
+        n = ents[0].shape[0]
+        if len(all_index) != n or (n > 0 and (all_index[0] != 0 or all_index[-1] != n - 1)):
+            idx = JF.as_index(all_index, ents[0].device)
+            ents = [e[idx] for e in ents]
+        return JF.l1_dist(ents[:L], rels[:L], e_index, r_index, pred_head)
+
+    def completion_loss(self, data, edge_index1, edge_type1, edge_index2, edge_type2, feeddict, source=True):
+        """:316-380."""
+        links = feeddict["links"]
+        _, ents1, rels1 = self.forward_base(edge_index1, edge_type1, feeddict["ent_bases1"], feeddict["rel_bases1"])
+        _, ents2, rels2 = self.forward_base(edge_index2, edge_type2, feeddict["ent_bases2"], feeddict["rel_bases2"])
+        L = self.args.num_gcn_layer
+        ents, rels = (ents1, rels1) if source else (ents2, rels2)
+        per_layer = JF.transe_margin_loss(list(ents[:L]), list(rels[:L]), data["batch_h"], data["batch_r"], data["batch_t"],
+                                          self.args.batch_size, self._margin())
+        loss = per_layer.sum().view(1)      # the reference's loss has shape [1] (margin Parameter broadcast, :374)
+        for layer in range(L):
+            loss = loss + self.alignment_loss_simple(links, ents1[layer], ents2[layer])
+        return loss
+
+    def _margin(self) -> float:
+        # margin_completion is a frozen Parameter (:156-157); cache its value to avoid a device sync per step
+        m = getattr(self, "_margin_cache", None)
+        if m is None:
+            m = float(self.margin_completion.detach().cpu().item())
+            self._margin_cache = m
+        return m

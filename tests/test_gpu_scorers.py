@@ -1,0 +1,225 @@
+"""GPU parity of the completion scorer, pair cosine, link prediction kernels and of the JMAC
+drop-in's losses / evaluator against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jmac_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def make_args(d, **kw):
+    from types import SimpleNamespace
+    a = SimpleNamespace(dim=d, device="cuda", dropout=0.0, leaky_relu_w=0.05, comp_op="sub", margin_align=1.0, num_negative=3,
+                        margin_completion=5.0, num_gcn_layer=2, no_name_info=True, batch_size=8)
+    a.__dict__.update(kw)
+    return a
+
+
+@pytest.mark.parametrize("N,R,d,B,K,tiled", [(500, 17, 256, 64, 25, True), (300, 5, 300, 33, 7, True), (200, 4, 64, 16, 70, False),
+                                              (100, 3, 32, 1, 1, True)])
+def test_transe_margin_matches_oracle(N, R, d, B, K, tiled):
+    from jmac_b200 import functional as JF
+    rng = np.random.default_rng(B * 131 + K)
+    torch.manual_seed(B)
+    ents = [torch.randn(N, d) for _ in range(2)]
+    rels = [torch.randn(R, d) for _ in range(2)]
+    M = (K + 1) * B
+    if tiled:   # train.py:347-352
+        h = np.tile(rng.integers(0, N, B), K + 1)
+        r = np.tile(rng.integers(0, R, B), K + 1)
+    else:       # arbitrary batch_h / batch_r (general contract of completion_loss)
+        h, r = rng.integers(0, N, M), rng.integers(0, R, M)
+    t = rng.integers(0, N, M)
+    margin = 5.0
+    ge = [e.cuda().requires_grad_(True) for e in ents]
+    gr = [x.cuda().requires_grad_(True) for x in rels]
+    loss = JF.transe_margin_loss(ge, gr, T(h), T(r), T(t), B, margin)
+    w = torch.tensor([0.7, 1.3], device="cuda")
+    (loss * w).sum().backward()
+    oe = [e.double().requires_grad_(True) for e in ents]
+    orr = [x.double().requires_grad_(True) for x in rels]
+    ol = torch.stack([O.transe_margin(oe[l], orr[l], T(h), T(r), T(t), B, margin)[0].reshape(()) for l in range(2)])
+    (ol * w.cpu().double()).sum().backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), ol.detach().numpy(), rtol=1e-5)
+    for l in range(2):
+        np.testing.assert_allclose(ge[l].grad.cpu().numpy(), oe[l].grad.numpy(), atol=1e-6, rtol=1e-4)
+        np.testing.assert_allclose(gr[l].grad.cpu().numpy(), orr[l].grad.numpy(), atol=1e-6, rtol=1e-4)
+
+
+def test_transe_bad_layout_raises_like_reference():
+    from jmac_b200 import functional as JF
+    e = [torch.randn(10, 32).cuda()]
+    r = [torch.randn(3, 32).cuda()]
+    idx = torch.zeros(14, dtype=torch.long)
+    with pytest.raises(RuntimeError):          # 14 triples cannot be viewed as [-1, 4] after the 4 positives
+        JF.transe_margin_loss(e, r, idx, idx, idx, 4, 5.0)
+
+
+@pytest.mark.parametrize("d", [32, 256, 300])
+def test_pair_cos_matches_oracle(d):
+    from jmac_b200 import functional as JF
+    rng = np.random.default_rng(d)
+    torch.manual_seed(d)
+    A, B = torch.randn(200, d), torch.randn(150, d)
+    A[3] = 0                                             # zero row: F.normalize clamps at 1e-12
+    ia, ib = rng.integers(0, 200, 400), rng.integers(0, 150, 400)
+    ia[0] = 3
+    g = torch.randn(400)
+    Ag, Bg = A.cuda().requires_grad_(True), B.cuda().requires_grad_(True)
+    cosv = JF.pair_cos(Ag, Bg, ia.astype(np.float64), T(ib))          # float64 indices as train.py:189-192 produces
+    (cosv * g.cuda()).sum().backward()
+    Ao, Bo = A.double().requires_grad_(True), B.double().requires_grad_(True)
+    co = (torch.nn.functional.normalize(Ao[T(ia)], 2, -1) * torch.nn.functional.normalize(Bo[T(ib)], 2, -1)).sum(1)
+    (co * g.double()).sum().backward()
+    np.testing.assert_allclose(cosv.detach().cpu().numpy(), co.detach().numpy(), atol=1e-6, rtol=1e-5)
+    np.testing.assert_allclose(Ag.grad.cpu().numpy(), Ao.grad.numpy(), atol=2e-6, rtol=1e-4)
+    np.testing.assert_allclose(Bg.grad.cpu().numpy(), Bo.grad.numpy(), atol=2e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N,d,B", [(1000, 256, 130), (333, 300, 7), (129, 32, 257)])
+def test_l1_dist_and_rank_match_oracle(N, d, B):
+    from jmac_b200 import functional as JF
+    rng = np.random.default_rng(N)
+    torch.manual_seed(N)
+    R = 6
+    ents = [torch.randn(N, d), torch.randn(N, d)]
+    rels = [torch.randn(R, d), torch.randn(R, d)]
+    e, r, t = rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)
+    ce, cr = [x.cuda() for x in ents], [x.cuda() for x in rels]
+    for pred_head in (False, True):
+        dist = JF.l1_dist(ce, cr, e.tolist(), r.tolist(), pred_head)
+        od = O.forward_linkpred(ents, rels, e, r, pred_head)
+        np.testing.assert_allclose(dist.cpu().numpy(), od.numpy(), rtol=2e-6, atol=1e-4)
+    # filtered ranks: CSR filter lists (true tails), the target is always among them
+    true_tail = {}
+    for j in range(B):
+        extra = rng.integers(0, N, rng.integers(0, 6))
+        true_tail[(int(e[j]), int(r[j]))] = np.unique(np.concatenate([true_tail.get((int(e[j]), int(r[j])), np.zeros(0, np.int64)), extra, [t[j]]]).astype(np.int64))
+    lists = [true_tail[(int(e[j]), int(r[j]))] for j in range(B)]
+    fptr = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+    fidx = np.concatenate(lists)
+    # (1) against the reference's sort-based ranking applied to the kernel's own fp32 distances:
+    #     bit-exact (rank-by-counting == position in the descending sort when there are no exact ties)
+    pred32 = -JF.l1_dist(ce, cr, e, r).cpu()
+    # (2) against the fp64 oracle: identical except for documented ties, i.e. competitors whose
+    #     distance is within 1e-5 relative of the target's (fp32 rounding can order them either way)
+    pred64 = -O.forward_linkpred([x.double() for x in ents], [x.double() for x in rels], e, r)
+    for filt in (True, False):
+        ranks = JF.l1_rank(ce, cr, e, r, t, fptr if filt else None, fidx if filt else None).cpu().numpy()
+        assert np.array_equal(ranks, O.linkpred_ranks(pred32, e, r, t, true_tail if filt else None))
+        oranks = O.linkpred_ranks(pred64, e, r, t, true_tail if filt else None)
+        tgt = pred64[torch.arange(B), T(t)]
+        near = ((pred64 - tgt[:, None]).abs() <= 1e-5 * tgt.abs()[:, None]).sum(1).numpy() - 1
+        assert np.all(np.abs(ranks - oranks) <= near)
+
+
+def model_pair(g, d_model_args):
+    from jmac_b200 import JMAC
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd.")}
+    n_ent = sd["ent_init_att_completion"].shape[0]
+    model = JMAC(d_model_args, np.zeros((n_ent, 300), dtype=np.float32), sd["rel_init_att_completion"].shape[0], n_ent).cuda()
+    missing = model.load_state_dict(sd, strict=True)
+    return model
+
+
+def test_state_dict_keys_match_reference(golden):
+    g = golden("model_noname")
+    ref_keys = sorted(k[3:] for k in g if k.startswith("sd."))
+    model = model_pair(g, make_args(16))
+    assert sorted(model.state_dict().keys()) == ref_keys
+
+
+@pytest.mark.parametrize("source", [True, False])
+def test_completion_loss_matches_reference_golden(golden, source):
+    g = golden("model_noname")
+    n1, n2, nr, B, K = (int(g[k]) for k in ("n1", "n2", "nr", "B", "K"))
+    model = model_pair(g, make_args(16, num_negative=K, batch_size=B))
+    model.train()
+    fd = {"links": g["links"], "ent_bases1": [0, n1], "ent_bases2": [n1, n1 + n2], "rel_bases1": [0, nr], "rel_bases2": [nr, 2 * nr]}
+    h, r = np.tile(g["sub"], K + 1), np.tile(g["rel"], K + 1)
+    t = np.concatenate([g["obj"], g["neg"].reshape(-1)])
+    if not source:
+        h, t = h % n2, t % n2
+    data = {"batch_h": T(h).cuda(), "batch_r": T(r).cuda(), "batch_t": T(t).cuda()}
+    loss = model.completion_loss(data, T(g["ei1"]).cuda(), T(g["et1"]).cuda(), T(g["ei2"]).cuda(), T(g["et2"]).cuda(), fd, source)
+    tag = "src" if source else "dst"
+    np.testing.assert_allclose(loss.item(), float(g["closs_" + tag].reshape(-1)[0]), rtol=1e-4)
+    loss.backward()
+    for k, v in g.items():
+        if k.startswith(f"cgrad_{tag}."):
+            name = k.split(".", 1)[1]
+            p = dict(model.named_parameters())[name]
+            got = np.zeros_like(v) if p.grad is None else p.grad.cpu().numpy()
+            scale = max(float(np.abs(v).max()), 1e-3)
+            assert float(np.abs(got - v).max()) <= 5e-3 * scale + 2e-5, name
+
+
+def test_alignment_loss_linkpred_getemb_match_reference_golden(golden):
+    g = golden("model_noname")
+    n1, n2, nr, B, K = (int(g[k]) for k in ("n1", "n2", "nr", "B", "K"))
+    model = model_pair(g, make_args(16, num_negative=K, batch_size=B))
+    model.train()
+    fa = {"links": g["links"], "ent_bases1": [0, n1], "ent_bases2": [n1, n1 + n2], "rel_bases1": [0, nr], "rel_bases2": [nr, 2 * nr],
+          "neg_left": g["fa.neg_left"], "neg_right": T(g["fa.neg_right"]), "neg2_left": T(g["fa.neg2_left"]), "neg2_right": g["fa.neg2_right"]}
+    ei1, et1, ei2, et2 = (T(g[k]).cuda() for k in ("ei1", "et1", "ei2", "et2"))
+    loss = model.alignment_loss(fa, ei1, et1, ei2, et2)
+    np.testing.assert_allclose(loss.item(), float(g["aloss"]), rtol=1e-4)
+    loss.backward()
+    for k, v in g.items():
+        if k.startswith("agrad."):
+            name = k.split(".", 1)[1]
+            p = dict(model.named_parameters())[name]
+            got = np.zeros_like(v) if p.grad is None else p.grad.cpu().numpy()
+            scale = max(float(np.abs(v).max()), 1e-3)
+            assert float(np.abs(got - v).max()) <= 5e-3 * scale + 2e-5, name
+    # empty links: python 0, as the reference (src/jmac_model.py:241-242,257-258)
+    assert model.alignment_loss({**fa, "links": []}, ei1, et1, ei2, et2) == 0
+    assert model.alignment_loss_simple([], None, None) == 0
+    # eval mode: link prediction + get_emb
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd.")}
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        dist = model.forward_linkpred(g["lp_e"].tolist(), g["lp_r"].tolist(), ei1, et1, list(range(n1)), [0, n1], [0, nr])
+        dh = model.forward_linkpred(g["lp_e"].tolist(), g["lp_r"].tolist(), ei1, et1, list(range(n1)), [0, n1], [0, nr], pred_head=True)
+        ea, ec = model.get_emb(ei1, et1, [0, n1], [0, nr])
+    np.testing.assert_allclose(dist.cpu().numpy(), g["lp_dist"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(dh.cpu().numpy(), g["lp_dist_head"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ec, g["emb_comp"], atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(ea, g["emb_align"], atol=1e-5, rtol=1e-4)
+
+
+def test_completion_evaluator_matches_reference_golden(golden):
+    """Same metrics as the reference's CompletionEvaluator.test on a small KG, val/test x raw/filtered."""
+    from types import SimpleNamespace
+    from jmac_b200 import CompletionEvaluator
+    g = golden("evaluator")
+    n, nr = int(g["n"]), int(g["nr"])
+    model = model_pair(g, make_args(16, batch_size=16))
+    model.eval()
+    allt = np.concatenate([g["train"], g["val"], g["test"]])
+    true_tail = {}
+    for h, r, t in allt:
+        true_tail.setdefault((int(h), int(r)), set()).add(int(t))
+
+    def gen(h, r, t, batch_size, shuffle=False):
+        tri = torch.stack([h, r, t], 1)
+        return [tri[i:i + batch_size] for i in range(0, len(tri), batch_size)]
+
+    kg = SimpleNamespace(edge_index=g["ei"], edge_type=g["et"], entity_id_base=0, upper_entity_base=n, relation_id_base=0,
+                         upper_relation_base=nr, true_tail={k: np.array(sorted(v)) for k, v in true_tail.items()}, num_entity=n,
+                         h_val=T(g["val"][:, 0]), r_val=T(g["val"][:, 1]), t_val=T(g["val"][:, 2]),
+                         h_test=T(g["test"][:, 0]), r_test=T(g["test"][:, 1]), t_test=T(g["test"][:, 2]), generate_batch_data=gen)
+    ev = CompletionEvaluator(kg, model, "cuda", None)
+    args = make_args(16, batch_size=16)
+    with torch.no_grad():
+        for is_val in (1, 0):
+            for filt in (1, 0):
+                got = ev.test(args, is_val=bool(is_val), filterr=bool(filt))
+                np.testing.assert_allclose(got, g[f"metrics_val{is_val}_filt{filt}"], rtol=1e-6)
