@@ -156,6 +156,31 @@ int jmac_l1_rank(const float* const* ent, const float* const* rel, int n_layers,
                  int64_t N, int pred_head, const int64_t* filt_ptr, const int64_t* filt_idx,
                  int32_t* rank, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Alignment scorer: similarity GEMM on the 5th-gen tensor cores with a streaming epilogue
+ * (modules/finding/similarity.py:13-84 sim / csls_sim / calculate_nearest_k,
+ *  modules/finding/alignment.py:87-112 calculate_rank, modules/utils/util.py:31-54 get_neg).
+ * The n1 x n2 matrix is never materialised.
+ * ------------------------------------------------------------------------------------------ */
+/* fp32 rows src[idx[r]] (idx NULL = identity), optionally L2-normalised (cosine metric), rounded to
+ * bf16 and zero-padded to dpad (multiple of 64) columns: dst[n_rows, dpad]. */
+int jmac_to_bf16_rows(const float* src, int d, const int64_t* idx, int64_t n_rows, int normalize,
+                      uint16_t* dst, int dpad, void* stream);
+/* S = A . B^T (bf16 inputs [n1,dpad], [n2,dpad], fp32 accumulation); per row i of A, over all j:
+ *   v_ij = (alpha * S_ij - r1[i]) - r2[j]            (r1, r2 may be NULL = 0)
+ *   topv/topi[n1,k] : the k largest v_ij, descending, ties -> lower j     (k = 0: skipped, k <= 32)
+ *   gold_cnt[i]     : #{ j : v_ij > gold_val[i] }                          (NULL: skipped)
+ *   diag[i]         : raw S at column gold_col[i]                           (NULL: skipped)
+ * dpad <= 256. */
+int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, int dpad, int k,
+                  float alpha, const float* r1, const float* r2, const int32_t* gold_col,
+                  const float* gold_val, int32_t* gold_cnt, float* diag, float* topv,
+                  int32_t* topi, void* stream);
+/* out[i] = (alpha * diag[i] - r1[i]) - r2[gold_col[i]], with the exact operation order of the
+ * epilogue above, so that the gold entry never counts as greater than itself. */
+int jmac_csls_gold(float alpha, const float* diag, const float* r1, const float* r2,
+                   const int32_t* gold_col, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,419 @@
+// Alignment similarity: S = E1 . E2^T as a bf16 tcgen05 GEMM (fp32 accumulation in TMEM) with a fused
+// STREAMING epilogue -- the n1 x n2 matrix is never written.  One kernel serves
+//   * sim + calculate_nearest_k (modules/finding/similarity.py:13-84): row top-k values (-> r1, r2),
+//   * csls_sim + calculate_rank   (similarity.py:58-78, alignment.py:87-112): v = 2S - r1[i] - r2[j],
+//     rank of the gold column by counting v > v_gold, optional top-k of v,
+//   * get_neg (modules/utils/util.py:31-54): row top-k indices,
+//   * the diagonal / gold-column raw similarity (needed to form v_gold bit-consistently).
+//
+// Shape of the machine (B200, sm_100a):
+//   CTA = 320 threads: warp 0 TMA producer, warp 1 tcgen05.mma issuer (+TMEM allocator), warps 2..9
+//   epilogue (one thread per output row, 256 rows per CTA).
+//   A block: 256 rows of E1 x K(<=256) bf16, resident in shared memory for a whole row sweep (128 KB).
+//   B tiles: 128 rows of E2, streamed as 64-wide K slices through a 6-slot TMA ring (16 KB each).
+//   MMA: cta_group::1, M=128 (two row halves), N=128, K=16, accumulators double-buffered in TMEM
+//   (2 stages x 2 halves x 128 columns = all 512 columns).
+//   Per 256x128 output tile: 2*16 MMAs = 2048 tensor cycles; B traffic 32 B/cycle/SM (L2-resident).
+//   The epilogue owns one row per thread, keeps its running top-k in registers across the whole sweep
+//   (no cross-CTA merge) and reads accumulators with tcgen05.ld 32x32b.x32.
+// Shared-memory operands use the canonical K-major SWIZZLE_128B layout written by TMA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace jmac {
+
+constexpr int SIM_BM = 256, SIM_BN = 128, SIM_BK = 64, SIM_NS = 6;
+constexpr int SIM_A_SLICE = SIM_BM * SIM_BK * 2;   // 32 KB
+constexpr int SIM_B_SLICE = SIM_BN * SIM_BK * 2;   // 16 KB
+constexpr int SIM_MAX_KS = 4;                       // K <= 256
+constexpr int SIM_THREADS = 320;
+constexpr int SIM_SMEM = SIM_MAX_KS * SIM_A_SLICE + SIM_NS * SIM_B_SLICE + 1024 /*align*/ + 256 /*barriers*/;
+
+struct SimParams {
+    int n1, n2, nks, k;
+    float alpha;
+    const float* r1;
+    const float* r2;
+    const int* gold_col;
+    const float* gold_val;
+    int* gold_cnt;
+    float* diag;
+    float* topv;
+    int* topi;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2),
+// 8-row groups 1024 B apart.  Advancing K by 16 bf16 = +32 B on the start address.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+    d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+    return d;
+}
+
+template <int KMAX>
+struct TopK {
+    float v[KMAX];
+    int i[KMAX];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) { v[j] = -INFINITY; i[j] = -1; }
+    }
+    // sorted descending; strict '>' keeps the earlier (lower) column on exact ties
+    __device__ __forceinline__ void insert(float x, int col) {
+#pragma unroll
+        for (int j = KMAX - 1; j >= 1; --j) {
+            const bool up = x > v[j - 1];
+            const bool here = !up && x > v[j];
+            i[j] = up ? i[j - 1] : (here ? col : i[j]);
+            v[j] = up ? v[j - 1] : (here ? x : v[j]);
+        }
+        if (x > v[0]) { v[0] = x; i[0] = col; }
+    }
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(SIM_THREADS, 1)
+sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, SimParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
+    const uint32_t smem_a = base;
+    const uint32_t smem_b = base + SIM_MAX_KS * SIM_A_SLICE;
+    const uint32_t bars = smem_b + SIM_NS * SIM_B_SLICE;
+    // barrier map (8 B each)
+    const uint32_t full0 = bars, empty0 = bars + 8 * SIM_NS, a_full = bars + 16 * SIM_NS, a_empty = a_full + 8;
+    const uint32_t t_full0 = a_empty + 8, t_empty0 = t_full0 + 16, tmem_slot = t_empty0 + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_rb = (p.n1 + SIM_BM - 1) / SIM_BM;
+    const int n_ct = (p.n2 + SIM_BN - 1) / SIM_BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SIM_NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full0 + 8 * s, 1); mbar_init(t_empty0 + 8 * s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0, rcount = 0;
+            for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++rcount) {
+                mbar_wait(a_empty, (rcount & 1) ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)p.nks * SIM_A_SLICE);
+                for (int ks = 0; ks < p.nks; ++ks) tma_load_2d(smem_a + ks * SIM_A_SLICE, &map_a, a_full, ks * SIM_BK, rb * SIM_BM);
+                for (int ct = 0; ct < n_ct; ++ct) {
+                    for (int ks = 0; ks < p.nks; ++ks, ++it) {
+                        const uint32_t slot = it % SIM_NS, ph = (it / SIM_NS) & 1;
+                        mbar_wait(empty0 + 8 * slot, ph ^ 1);
+                        mbar_expect_tx(full0 + 8 * slot, SIM_B_SLICE);
+                        tma_load_2d(smem_b + slot * SIM_B_SLICE, &map_b, full0 + 8 * slot, ks * SIM_BK, ct * SIM_BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // kind::f16, A=B=BF16, D=F32, both K-major, M=128, N=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SIM_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t it = 0, tcount = 0, rcount = 0;
+            for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++rcount) {
+                mbar_wait(a_full, rcount & 1);
+                tc_fence_after();
+                for (int ct = 0; ct < n_ct; ++ct, ++tcount) {
+                    const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                    mbar_wait(t_empty0 + 8 * acc, aph ^ 1);
+                    tc_fence_after();
+                    for (int ks = 0; ks < p.nks; ++ks, ++it) {
+                        const uint32_t slot = it % SIM_NS, ph = (it / SIM_NS) & 1;
+                        mbar_wait(full0 + 8 * slot, ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = umma_desc(smem_b + slot * SIM_B_SLICE);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const uint64_t adesc = umma_desc(smem_a + ks * SIM_A_SLICE + half * (128 * 128));
+                            const uint32_t d_tmem = tmem_base + acc * 256 + half * 128;
+#pragma unroll
+                            for (int kk = 0; kk < SIM_BK / 16; ++kk)
+                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (ks | kk) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(empty0 + 8 * slot);     // slot reusable once these MMAs retire
+                    }
+                    tc_commit(t_full0 + 8 * acc);         // accumulators of this tile complete
+                }
+                tc_commit(a_empty);                        // A block may be overwritten
+            }
+        }
+    } else {
+        // ===================== epilogue: one thread per output row =====================
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;
+        const int row_in_blk = half * 128 + quarter * 32 + lane;
+        const bool want_topk = p.k > 0;
+        uint32_t tcount = 0;
+        for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+            const int row = rb * SIM_BM + row_in_blk;
+            const bool rvalid = row < p.n1;
+            TopK<KMAX> tk;
+            tk.init();
+            const float r1 = (p.r1 && rvalid) ? p.r1[row] : 0.f;
+            const float gold = (p.gold_val && rvalid) ? p.gold_val[row] : INFINITY;
+            const int gcol = (p.gold_col && rvalid) ? p.gold_col[row] : -1;
+            int cnt = 0;
+            float dg = 0.f;
+            for (int ct = 0; ct < n_ct; ++ct, ++tcount) {
+                const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(t_full0 + 8 * acc, aph);
+                tc_fence_after();
+                const bool ragged = (ct + 1) * SIM_BN > p.n2;
+#pragma unroll 1
+                for (int c0 = 0; c0 < SIM_BN; c0 += 32) {
+                    uint32_t raw[32];
+                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128 + c0, raw);
+                    const int col0 = ct * SIM_BN + c0;
+                    if (col0 >= p.n2) break;                       // uniform
+                    if (p.diag && gcol >= col0 && gcol < col0 + 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j == gcol) dg = __uint_as_float(raw[j]);
+                    }
+                    float v[32];
+                    if (p.r2) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            float4 rr;
+                            if (!ragged) rr = __ldg(reinterpret_cast<const float4*>(p.r2 + col0) + j4);
+                            else {
+                                rr.x = col0 + 4 * j4 + 0 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 0) : 0.f;
+                                rr.y = col0 + 4 * j4 + 1 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 1) : 0.f;
+                                rr.z = col0 + 4 * j4 + 2 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 2) : 0.f;
+                                rr.w = col0 + 4 * j4 + 3 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 3) : 0.f;
+                            }
+                            v[4 * j4 + 0] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 0]), -r1), rr.x);
+                            v[4 * j4 + 1] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 1]), -r1), rr.y);
+                            v[4 * j4 + 2] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 2]), -r1), rr.z);
+                            v[4 * j4 + 3] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 3]), -r1), rr.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __fmaf_rn(p.alpha, __uint_as_float(raw[j]), -r1);
+                    }
+                    if (ragged) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j >= p.n2) v[j] = -INFINITY;
+                    }
+                    if (p.gold_cnt) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cnt += (v[j] > gold) ? 1 : 0;
+                    }
+                    if (want_topk) {
+                        float m = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                        if (m > tk.v[KMAX - 1]) {               // rare after the first few tiles
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (v[j] > tk.v[KMAX - 1]) tk.insert(v[j], col0 + j);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty0 + 8 * acc);
+            }
+            if (rvalid) {
+                if (want_topk) {
+#pragma unroll
+                    for (int j = 0; j < KMAX; ++j)
+                        if (j < p.k) { p.topv[(size_t)row * p.k + j] = tk.v[j]; p.topi[(size_t)row * p.k + j] = tk.i[j]; }
+                }
+                if (p.gold_cnt) p.gold_cnt[row] = cnt;
+                if (p.diag) p.diag[row] = dg;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// fp32 rows (optionally gathered by idx, optionally L2-normalised) -> bf16 rows padded to dpad columns
+__global__ void to_bf16_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_rows, int d, int dpad,
+                                    int normalize, uint16_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const float* s = src + (idx ? idx[r] : r) * (int64_t)d;
+    float scale = 1.f;
+    if (normalize) {
+        float ss = 0.f;
+        for (int c = lane; c < d; c += 32) ss = fmaf(s[c], s[c], ss);
+        ss = warp_sum(ss);
+        scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    for (int c = lane; c < dpad; c += 32) {
+        const float v = c < d ? s[c] * scale : 0.f;
+        dst[r * dpad + c] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+}
+
+__global__ void csls_gold_kernel(float alpha, const float* __restrict__ diag, const float* __restrict__ r1, const float* __restrict__ r2,
+                                 const int* __restrict__ gold_col, int64_t n, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = __fmaf_rn(alpha, diag[i], r1 ? -r1[i] : -0.f);
+    if (r2) v = __fsub_rn(v, r2[gold_col[i]]);
+    out[i] = v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dpad, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return JMAC_EINVAL; }
+    cuuint64_t dims[2] = {(cuuint64_t)dpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)dpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)SIM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return JMAC_EINVAL; }
+    return 0;
+}
+
+}  // namespace jmac
+
+using namespace jmac;
+
+extern "C" int jmac_to_bf16_rows(const float* src, int d, const int64_t* idx, int64_t n_rows, int normalize, uint16_t* dst, int dpad,
+                                 void* stream) {
+    JMAC_ARG(src && dst && d > 0 && dpad >= d && (dpad % 64) == 0 && n_rows >= 0);
+    if (n_rows == 0) return 0;
+    const int64_t blocks = (n_rows * 32 + 255) / 256;
+    to_bf16_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, n_rows, d, dpad, normalize, dst);
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int jmac_csls_gold(float alpha, const float* diag, const float* r1, const float* r2, const int32_t* gold_col, int64_t n,
+                              float* out, void* stream) {
+    JMAC_ARG(diag && out && n >= 0 && (r2 == nullptr || gold_col != nullptr));
+    if (n == 0) return 0;
+    csls_gold_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(alpha, diag, r1, r2, gold_col, n, out);
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, int dpad, int k, float alpha, const float* r1,
+                             const float* r2, const int32_t* gold_col, const float* gold_val, int32_t* gold_cnt, float* diag, float* topv,
+                             int32_t* topi, void* stream) {
+    JMAC_ARG(A && B && n1 > 0 && n2 > 0 && n1 < (int64_t(1) << 31) && n2 < (int64_t(1) << 31));
+    JMAC_ARG(dpad >= 64 && dpad <= SIM_MAX_KS * SIM_BK && (dpad % 64) == 0);
+    JMAC_ARG(k >= 0 && k <= 32 && (k == 0 || (topv && topi)));
+    JMAC_ARG((gold_cnt == nullptr) || gold_val != nullptr);
+    JMAC_ARG((diag == nullptr) || gold_col != nullptr);
+    JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0);
+    JMAC_ARG(r2 == nullptr || ((uintptr_t)r2 % 16) == 0);
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, A, n1, dpad, SIM_BM);
+    if (rc) return rc;
+    rc = make_map(&map_b, B, n2, dpad, SIM_BN);
+    if (rc) return rc;
+    SimParams p;
+    p.n1 = (int)n1; p.n2 = (int)n2; p.nks = dpad / SIM_BK; p.k = k; p.alpha = alpha; p.r1 = r1; p.r2 = r2;
+    p.gold_col = gold_col; p.gold_val = gold_val; p.gold_cnt = gold_cnt; p.diag = diag; p.topv = topv; p.topi = topi;
+    const int n_rb = (int)((n1 + SIM_BM - 1) / SIM_BM);
+    const int grid = n_rb < sm_count() ? n_rb : sm_count();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 16) {
+        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM));
+        sim_topk_kernel<16><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);
+    } else {
+        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM));
+        sim_topk_kernel<32><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);
+    }
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}
