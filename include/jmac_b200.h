@@ -167,7 +167,8 @@ int jmac_l1_rank(const float* const* ent, const float* const* rel, int n_layers,
 int jmac_to_bf16_rows(const float* src, int d, const int64_t* idx, int64_t n_rows, int normalize,
                       uint16_t* dst, int dpad, void* stream);
 /* S = A . B^T (bf16 inputs [n1,dpad], [n2,dpad], fp32 accumulation); per row i of A, over all j:
- *   v_ij = (alpha * S_ij - r1[i]) - r2[j]            (r1, r2 may be NULL = 0)
+ *   v_ij = (alpha * S_ij - r1[i]) - r2[j]            (r1, r2 may be NULL = 0; r2 must be readable up to
+ *                                                      the next multiple of 128 entries, 16-byte aligned)
  *   topv/topi[n1,k] : the k largest v_ij, descending, ties -> lower j     (k = 0: skipped, k <= 32)
  *   gold_cnt[i]     : #{ j : v_ij > gold_val[i] }                          (NULL: skipped)
  *   diag[i]         : raw S at column gold_col[i]                           (NULL: skipped)

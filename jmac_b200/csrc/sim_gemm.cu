@@ -30,7 +30,8 @@ constexpr int SIM_A_SLICE = SIM_BM * SIM_BK * 2;   // 32 KB
 constexpr int SIM_B_SLICE = SIM_BN * SIM_BK * 2;   // 16 KB
 constexpr int SIM_MAX_KS = 4;                       // K <= 256
 constexpr int SIM_THREADS = 320;
-constexpr int SIM_SMEM = SIM_MAX_KS * SIM_A_SLICE + SIM_NS * SIM_B_SLICE + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SIM_SMEM = SIM_MAX_KS * SIM_A_SLICE + SIM_NS * SIM_B_SLICE + 1024 /*align*/ + 256 /*barriers*/ + 2 * SIM_BN * 4 /*r2 ring*/;
+static_assert(SIM_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct SimParams {
     int n1, n2, nks, k;
@@ -82,7 +83,8 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -92,7 +94,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2),
@@ -128,7 +134,7 @@ struct TopK {
     }
 };
 
-template <int KMAX>
+template <int KMAX, bool CSLS>
 __global__ void __launch_bounds__(SIM_THREADS, 1)
 sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, SimParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -139,6 +145,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // barrier map (8 B each)
     const uint32_t full0 = bars, empty0 = bars + 8 * SIM_NS, a_full = bars + 16 * SIM_NS, a_empty = a_full + 8;
     const uint32_t t_full0 = a_empty + 8, t_empty0 = t_full0 + 16, tmem_slot = t_empty0 + 16;
+    const uint32_t r2_full0 = tmem_slot + 8, r2_empty0 = r2_full0 + 16, r2_slots = bars + 256;   // 2 x 512 B of r2, staged by TMA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_rb = (p.n1 + SIM_BM - 1) / SIM_BM;
@@ -148,6 +155,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int s = 0; s < SIM_NS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(a_full, 1); mbar_init(a_empty, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(t_full0 + 8 * s, 1); mbar_init(t_empty0 + 8 * s, 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(r2_full0 + 8 * s, 1); mbar_init(r2_empty0 + 8 * s, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -163,17 +171,25 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it = 0, rcount = 0;
+            uint32_t it = 0, rcount = 0, tcount = 0;
             for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++rcount) {
                 mbar_wait(a_empty, (rcount & 1) ^ 1);
                 mbar_expect_tx(a_full, (uint32_t)p.nks * SIM_A_SLICE);
                 for (int ks = 0; ks < p.nks; ++ks) tma_load_2d(smem_a + ks * SIM_A_SLICE, &map_a, a_full, ks * SIM_BK, rb * SIM_BM);
-                for (int ct = 0; ct < n_ct; ++ct) {
+                for (int ct = 0; ct < n_ct; ++ct, ++tcount) {
                     for (int ks = 0; ks < p.nks; ++ks, ++it) {
                         const uint32_t slot = it % SIM_NS, ph = (it / SIM_NS) & 1;
                         mbar_wait(empty0 + 8 * slot, ph ^ 1);
                         mbar_expect_tx(full0 + 8 * slot, SIM_B_SLICE);
                         tma_load_2d(smem_b + slot * SIM_B_SLICE, &map_b, full0 + 8 * slot, ks * SIM_BK, ct * SIM_BN);
+                    }
+                    if (CSLS) {
+                        // this tile's 128 column offsets r2[j] -> shared memory (r2 is padded to a multiple of 128).
+                        // Issued AFTER the tile's B slices so that waiting for the epilogue of tile t-2 never delays them.
+                        const uint32_t rs = tcount & 1, rph = (tcount >> 1) & 1;
+                        mbar_wait(r2_empty0 + 8 * rs, rph ^ 1);
+                        mbar_expect_tx(r2_full0 + 8 * rs, SIM_BN * 4);
+                        bulk_load_1d(r2_slots + rs * SIM_BN * 4, p.r2 + (size_t)ct * SIM_BN, SIM_BN * 4, r2_full0 + 8 * rs);
                     }
                 }
             }
@@ -217,6 +233,8 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int half = (warp - 2) >> 2;
         const int row_in_blk = half * 128 + quarter * 32 + lane;
         const bool want_topk = p.k > 0;
+        const bool want_cnt = p.gold_cnt != nullptr;
+        const float* r2_smem = reinterpret_cast<const float*>(smem_raw + (r2_slots - smem_u32(smem_raw)));
         uint32_t tcount = 0;
         for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
             const int row = rb * SIM_BM + row_in_blk;
@@ -225,52 +243,51 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tk.init();
             const float r1 = (p.r1 && rvalid) ? p.r1[row] : 0.f;
             const float gold = (p.gold_val && rvalid) ? p.gold_val[row] : INFINITY;
-            const int gcol = (p.gold_col && rvalid) ? p.gold_col[row] : -1;
+            const int gcol = (p.diag && rvalid) ? p.gold_col[row] : -1;
             int cnt = 0;
             float dg = 0.f;
             for (int ct = 0; ct < n_ct; ++ct, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                const uint32_t rs = tcount & 1, rph = (tcount >> 1) & 1;
                 mbar_wait(t_full0 + 8 * acc, aph);
+                if (CSLS) mbar_wait(r2_full0 + 8 * rs, rph);
                 tc_fence_after();
                 const bool ragged = (ct + 1) * SIM_BN > p.n2;
-#pragma unroll 1
-                for (int c0 = 0; c0 < SIM_BN; c0 += 32) {
-                    uint32_t raw[32];
-                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128 + c0, raw);
-                    const int col0 = ct * SIM_BN + c0;
-                    if (col0 >= p.n2) break;                       // uniform
-                    if (p.diag && gcol >= col0 && gcol < col0 + 32) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128;
+                const float* r2t = r2_smem + rs * SIM_BN;
+                uint32_t raw[2][32];
+                tc_ld32_issue(taddr, raw[0]);
+#pragma unroll
+                for (int c = 0; c < SIM_BN / 32; ++c) {
+                    tc_ld_wait();
+                    if (c + 1 < SIM_BN / 32) tc_ld32_issue(taddr + (c + 1) * 32, raw[(c + 1) & 1]);   // overlaps the math below
+                    const uint32_t(&rw)[32] = raw[c & 1];
+                    const int col0 = ct * SIM_BN + c * 32;
+                    if (gcol >= col0 && gcol < col0 + 32) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (col0 + j == gcol) dg = __uint_as_float(raw[j]);
+                            if (col0 + j == gcol) dg = __uint_as_float(rw[j]);
                     }
                     float v[32];
-                    if (p.r2) {
+                    if (CSLS) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            float4 rr;
-                            if (!ragged) rr = __ldg(reinterpret_cast<const float4*>(p.r2 + col0) + j4);
-                            else {
-                                rr.x = col0 + 4 * j4 + 0 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 0) : 0.f;
-                                rr.y = col0 + 4 * j4 + 1 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 1) : 0.f;
-                                rr.z = col0 + 4 * j4 + 2 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 2) : 0.f;
-                                rr.w = col0 + 4 * j4 + 3 < p.n2 ? __ldg(p.r2 + col0 + 4 * j4 + 3) : 0.f;
-                            }
-                            v[4 * j4 + 0] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 0]), -r1), rr.x);
-                            v[4 * j4 + 1] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 1]), -r1), rr.y);
-                            v[4 * j4 + 2] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 2]), -r1), rr.z);
-                            v[4 * j4 + 3] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(raw[4 * j4 + 3]), -r1), rr.w);
+                            const float4 rr = *reinterpret_cast<const float4*>(r2t + c * 32 + 4 * j4);   // LDS.128 broadcast
+                            v[4 * j4 + 0] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(rw[4 * j4 + 0]), -r1), rr.x);
+                            v[4 * j4 + 1] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(rw[4 * j4 + 1]), -r1), rr.y);
+                            v[4 * j4 + 2] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(rw[4 * j4 + 2]), -r1), rr.z);
+                            v[4 * j4 + 3] = __fsub_rn(__fmaf_rn(p.alpha, __uint_as_float(rw[4 * j4 + 3]), -r1), rr.w);
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __fmaf_rn(p.alpha, __uint_as_float(raw[j]), -r1);
+                        for (int j = 0; j < 32; ++j) v[j] = __fmaf_rn(p.alpha, __uint_as_float(rw[j]), -r1);
                     }
                     if (ragged) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (col0 + j >= p.n2) v[j] = -INFINITY;
                     }
-                    if (p.gold_cnt) {
+                    if (want_cnt) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) cnt += (v[j] > gold) ? 1 : 0;
                     }
@@ -279,15 +296,27 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
                         if (m > tk.v[KMAX - 1]) {               // rare after the first few tiles
+                            // compact slow path (one copy of the insertion code, not 32: keeps the I-cache footprint small)
+                            unsigned cand = 0u;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (v[j] > tk.v[KMAX - 1]) tk.insert(v[j], col0 + j);
+                            for (int j = 0; j < 32; ++j) cand |= (v[j] > tk.v[KMAX - 1] ? 1u : 0u) << j;
+                            while (cand) {
+                                const int j = __ffs(cand) - 1;
+                                cand &= cand - 1;
+                                float x = v[0];
+#pragma unroll
+                                for (int jj = 1; jj < 32; ++jj) x = (j == jj) ? v[jj] : x;
+                                if (x > tk.v[KMAX - 1]) tk.insert(x, col0 + j);
+                            }
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty0 + 8 * acc);
+                if (lane == 0) {
+                    mbar_arrive(t_empty0 + 8 * acc);
+                    if (CSLS) mbar_arrive(r2_empty0 + 8 * rs);
+                }
             }
             if (rvalid) {
                 if (want_topk) {
@@ -295,7 +324,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int j = 0; j < KMAX; ++j)
                         if (j < p.k) { p.topv[(size_t)row * p.k + j] = tk.v[j]; p.topi[(size_t)row * p.k + j] = tk.i[j]; }
                 }
-                if (p.gold_cnt) p.gold_cnt[row] = cnt;
+                if (want_cnt) p.gold_cnt[row] = cnt;
                 if (p.diag) p.diag[row] = dg;
             }
         }
@@ -407,13 +436,15 @@ extern "C" int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, i
     const int n_rb = (int)((n1 + SIM_BM - 1) / SIM_BM);
     const int grid = n_rb < sm_count() ? n_rb : sm_count();
     cudaStream_t st = (cudaStream_t)stream;
-    if (k <= 16) {
-        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM));
-        sim_topk_kernel<16><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);
-    } else {
-        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM));
-        sim_topk_kernel<32><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);
-    }
+#define JMAC_SIM_LAUNCH(KM, CS)                                                                                          \
+    do {                                                                                                                 \
+        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<KM, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM)); \
+        sim_topk_kernel<KM, CS><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);                                    \
+    } while (0)
+    if (k <= 1)       { if (r2) JMAC_SIM_LAUNCH(1, true);  else JMAC_SIM_LAUNCH(1, false); }
+    else if (k <= 16) { if (r2) JMAC_SIM_LAUNCH(16, true); else JMAC_SIM_LAUNCH(16, false); }
+    else              { if (r2) JMAC_SIM_LAUNCH(32, true); else JMAC_SIM_LAUNCH(32, false); }
+#undef JMAC_SIM_LAUNCH
     JMAC_LAUNCH_CHECK();
     return 0;
 }

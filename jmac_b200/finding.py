@@ -59,6 +59,11 @@ def sim_topk(A: torch.Tensor, B: torch.Tensor, k: int, alpha: float = 1.0, r1=No
     topi = torch.empty(n1, max(k, 1), dtype=torch.int32, device=dev) if k > 0 else None
     cnt = torch.empty(n1, dtype=torch.int32, device=dev) if want_count else None
     diag = torch.empty(n1, dtype=torch.float32, device=dev) if want_diag else None
+    if r2 is not None:
+        n2p = (n2 + 127) // 128 * 128            # the kernel stages r2 in 128-column tiles with a bulk copy
+        if r2.numel() < n2p:
+            r2 = torch.cat([r2.reshape(-1).float(), torch.zeros(n2p - r2.numel(), dtype=torch.float32, device=dev)])
+        r2 = r2.contiguous()
     with torch.cuda.device(dev):
         check(lib.jmac_sim_topk(ptr(A), ptr(B), n1, n2, dpad, int(k), float(alpha), ptr(r1), ptr(r2), ptr(gold_col), ptr(gold_val), ptr(cnt),
                                 ptr(diag), ptr(topv), ptr(topi), stream_ptr()), "jmac_sim_topk")
