@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the JMAC hot path on B200 (contract: see the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--sections a,b,...]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
 
 Headline workload (BASELINE.json configs[3], "C4"): synthetic KG with 2M entities, 2k relations,
 40M triples (uniform endpoints: no cache reuse, the honest HBM-bound case), d=256, two stacked
 relation-aware GNN layers forward+backward.  One step = one pass of both layers over the whole
-graph; value = layer-edges per second = (2 * E * steps) / time, whole job.
-Also reported on the same line (measured after the headline, not inside its timed region):
-  * "scorer": completion scorer fwd+bwd, B=65536 positives x K=64 negatives, 2 layers of tables;
-  * "roofline": the dominant edge kernel timed alone with CUDA events vs MEASURED_PEAKS.json;
-  * "cpu_baseline": the CPU oracle (port of the reference algorithm) on a bounded sample;
-  * "e2e": the same step through the public module API with HOST (pinned) inputs: H2D of
-    X, R, edge_index, edge_type + plan build + 2 layers fwd+bwd + D2H of the loss, every step.
---impl reference times the reference algorithm's CPU path (oracle port; /root/reference is pure
-Python and does not exist on the GPU box) on a bounded sample of the same workload.
+graph; value = layer-edges per second = (2 * E) / step time, whole job.  With N > 1 the SAME graph
+is destination-sharded over the ranks (strong scaling; halo all-gather / reduce-scatter over NCCL).
+
+Further sections on the same JSON line (each timed separately, after the headline region):
+  roofline     every edge kernel timed alone with CUDA events vs MEASURED_PEAKS.json (N=1)
+  scorer       completion scorer fwd+bwd, B=65536 positives x K=64 negatives, 2 layers (N=1)
+  align        alignment scorer: 1M x 1M x 256 bf16 similarity + CSLS(10) + Hits@k, row-sharded over
+               the ranks (BASELINE.json configs[4], "C5"); rows/s and tensor-pipe fraction
+  e2e          the headline step through the public module API from HOST (pinned) inputs: H2D of
+               X, R, edge_index, edge_type + plan build + 2 layers fwd+bwd + D2H of the loss (N=1)
+  cpu          cpu_baseline: the CPU oracle (port of the reference algorithm) on a bounded sample
+--impl reference times the reference algorithm's CPU path (the oracle port; /root/reference is pure
+Python, cannot be pip-installed and does not exist on the GPU box) on a bounded sample.
 """
 import argparse
 import json
@@ -28,16 +33,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D = 256
-FULL = dict(N=2_000_000, R=2_000, E=40_000_000, B=65_536, K=64)
+FULL = dict(N=2_000_000, R=2_000, E=40_000_000, B=65_536, K=64, ALIGN=1_048_576)
 CPU_SAMPLE = dict(N=50_000, R=2_000, E=1_000_000)      # same mean degree (20) and width as C4
+ALL_SECTIONS = ("roofline", "scorer", "align", "e2e", "cpu")
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), float(j["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -82,7 +88,6 @@ class ClockSampler:
 def cpu_layer_step(N, R, E, steps, warmup, seed=0):
     """The reference algorithm (oracle port, un-factored per-edge formulation) on host cores:
     one RelationAwareLayer forward+backward.  Returns (edges/s, seconds per step, threads)."""
-    import numpy as np
     import torch
     from oracle import jmac_oracle as O
     g = torch.Generator().manual_seed(seed)
@@ -111,6 +116,15 @@ def cpu_layer_step(N, R, E, steps, warmup, seed=0):
     return E / dt, dt, torch.get_num_threads()
 
 
+def workload_config(n_gpus, scale=1.0):
+    w = {k: (int(v * scale) if k in ("N", "E", "B", "ALIGN") else v) for k, v in FULL.items()}
+    w["ALIGN"] = max(256, w["ALIGN"] // 256 * 256)
+    return {"workload": "C4: synthetic KG, 2M entities, 2k relations, 40M triples (uniform), d=256, 2 stacked relation-aware GNN layers fwd+bwd",
+            "entities": w["N"], "relations": w["R"], "edges": w["E"], "dim": D, "layers": 2, "scorer_batch": w["B"], "negatives": w["K"],
+            "align_rows": w["ALIGN"], "parallelism": f"dst-shard x{n_gpus}" if n_gpus > 1 else "single",
+            "l2_policy": "inputs larger than L2 (tables 2 GB each), no flush"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -125,13 +139,6 @@ def run_reference(args):
             "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
-
-
-def workload_config(n_gpus, scale=1.0):
-    w = {k: (int(v * scale) if k in ("N", "E", "B") else v) for k, v in FULL.items()}
-    return {"workload": "C4: synthetic KG, 2M entities, 2k relations, 40M triples (uniform), d=256, 2 stacked relation-aware GNN layers fwd+bwd",
-            "entities": w["N"], "relations": w["R"], "edges": w["E"], "dim": D, "layers": 2, "scorer_batch": w["B"], "negatives": w["K"],
-            "parallelism": f"dst-shard x{n_gpus}" if n_gpus > 1 else "single", "l2_policy": "inputs larger than L2 (tables 2 GB each), no flush"}
 
 
 def event_time(fn, warmup, iters):
@@ -153,7 +160,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from types import SimpleNamespace
-    from jmac_b200 import RelationAwareLayer, _lib, functional as JF
+    from jmac_b200 import RelationAwareLayer, _lib, finding as JFind, functional as JF
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,10 +171,18 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    sections = set(ALL_SECTIONS if args.sections == "all" else [s for s in args.sections.split(",") if s])
     lib = _lib.load()
     cfg = workload_config(world, args.scale)
-    N, R, E, B, K = cfg["entities"], cfg["relations"], cfg["edges"], cfg["scorer_batch"], cfg["negatives"]
-    hbm_peak, peak_src = peaks()
+    N, R, E, B, K, NA = cfg["entities"], cfg["relations"], cfg["edges"], cfg["scorer_batch"], cfg["negatives"], cfg["align_rows"]
+    hbm_peak, tf_sust, tf_burst, peak_src = peaks()
+
+    def sync_max_ms(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     gen = torch.Generator(device=dev).manual_seed(0)
     ei = torch.randint(0, N, (2, E), device=dev, generator=gen)
@@ -183,6 +198,8 @@ def run_b200(args):
     if world > 1:
         from jmac_b200 import dist as JD
         runner = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD)
+        del ei, et
+        torch.cuda.empty_cache()
         step_fn = lambda: runner.step(x0, rel, gout)
     else:
         def step_fn():
@@ -200,26 +217,25 @@ def run_b200(args):
         dist.barrier()
     n0 = lib.jmac_launch_count()
     with ClockSampler(local) as clk:
+        torch.cuda.nvtx.range_push("timed")
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(args.steps):
             step_fn()
         e.record()
         torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
     launches = int(lib.jmac_launch_count() - n0)
-    ms = torch.tensor([s.elapsed_time(e)], device=dev)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    total_ms = sync_max_ms(s.elapsed_time(e))
     ms_per_step = total_ms / args.steps
     value = 2.0 * E / (ms_per_step * 1e-3)
 
     line = {"metric": "gnn_layer_edges_per_s_fwd_bwd", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg, "gpu_launches": launches, "clocks": clk.summary()}
+    single = world == 1
 
-    if rank == 0 and world == 1:
+    if single and "roofline" in sections:
         # ---- roofline of the edge kernels, each timed alone on the launching stream
         d = D
         plan = JF.get_plan(ei, et, N, R + 1)
@@ -254,12 +270,13 @@ def run_b200(args):
         edge_ms = sum(v["ms"] for v in kernels.values())
         edge_bytes = sum(v["algo_bytes"] for v in kernels.values())
         line["roofline"] = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                            "frac": kernels[top]["frac"], "traffic": None, "peak_source": peak_src,
+                            "frac": kernels[top]["frac"], "traffic": TRAFFIC_NCU.get(top), "peak_source": peak_src,
                             "edge_phase_fwd_bwd": {"ms": edge_ms, "GBps": edge_bytes / edge_ms / 1e6, "frac": edge_bytes / edge_ms / 1e6 / hbm_peak,
                                                    "edges_per_s": E / (edge_ms * 1e-3)},
                             "kernels": kernels}
-        del agg, lse, dP, dXe, dQ, erec
+        del agg, lse, dP, dXe, dQ, erec, P, Q
 
+    if single and "scorer" in sections:
         # ---- completion scorer, fwd+bwd, reference batch layout
         rng = np.random.default_rng(0)
         hh = torch.from_numpy(np.tile(rng.integers(0, N, B), K + 1)).to(dev)
@@ -275,16 +292,50 @@ def run_b200(args):
             loss.sum().backward()
         t = event_time(scorer_step, 3, 10)
         scored = (K + 1) * B
-        sbytes = 2 * 3 * (K + 3) * B * row
+        sbytes = 2 * 3 * (K + 3) * B * D * 4
         line["scorer"] = {"metric": "triples_scored_per_s_fwd_bwd", "value": scored / (t * 1e-3), "unit": "triples/s", "ms": t,
                           "batch": B, "negatives": K, "layers": 2, "algo_GBps": sbytes / t / 1e6, "frac_hbm": sbytes / t / 1e6 / hbm_peak,
                           "note": "includes zero-filling the two dense [N,d] gradient tables per layer (autograd semantics)"}
         del e_tabs, hh, rr, tt
 
+    if "align" in sections:
+        # ---- alignment scorer at scale (C5): bf16 similarity GEMM + CSLS(10) + Hits@k, rows sharded over ranks
+        ga = torch.Generator(device=dev).manual_seed(1)
+        e1 = torch.nn.functional.normalize(torch.randn(NA, D, device=dev, generator=ga))
+        e2 = torch.nn.functional.normalize(e1 + 2.5 * torch.nn.functional.normalize(torch.randn(NA, D, device=dev, generator=ga)))   # planted matches, cos(gold) ~ 0.37
+        A, Bm = JFind.to_bf16_rows(e1), JFind.to_bf16_rows(e2)
+        del e1, e2
+        grp = dist.group.WORLD if world > 1 else None
+        res = {}
+
+        def align_step():
+            res["ranks"], res["top1"] = JFind.alignment_ranks_bf16(A, Bm, csls_k=10, group=grp)
+        align_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s2, e2_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        align_step()
+        e2_.record()
+        torch.cuda.synchronize()
+        t = sync_max_ms(s2.elapsed_time(e2_))
+        ranks = res["ranks"].cpu().numpy()
+        flops = 6.0 * NA * NA * D
+        line["align"] = {"metric": "align_rows_per_s_csls_topk", "value": NA / (t * 1e-3), "unit": "rows/s", "ms": t, "rows": NA, "cols": NA,
+                         "passes": 3, "TFLOPs": flops / t / 1e9, "frac_tensor_sustained": flops / t / 1e9 / tf_sust / world,
+                         "frac_tensor_burst": flops / t / 1e9 / tf_burst / world,
+                         "hits@1": float((ranks < 1).mean()), "hits@10": float((ranks < 10).mean()), "mrr": float((1.0 / (ranks + 1)).mean())}
+        del A, Bm
+
+    if single and "e2e" in sections:
         # ---- e2e: HOST inputs every step (pinned), plan rebuilt, result read back
         h_x, h_r = x0.detach().cpu().pin_memory(), rel.detach().cpu().pin_memory()
         h_ei, h_et = ei.cpu().pin_memory(), et.cpu().pin_memory()
         h2d = h_x.numel() * 4 + h_r.numel() * 4 + h_ei.numel() * 8 + h_et.numel() * 8
+        del ei, et
+        JF.clear_plan_cache()
+        torch.cuda.empty_cache()
 
         def e2e_step():
             JF.clear_plan_cache()
@@ -297,22 +348,25 @@ def run_b200(args):
             loss = (h * gout).sum()
             loss.backward()
             return float(loss.item())
-        del ei, et
-        torch.cuda.empty_cache()
         t = event_time(e2e_step, 1, max(2, min(args.steps, 3)))
         line["e2e"] = {"value": 2.0 * E / (t * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": t,
                        "api": "jmac_b200.RelationAwareLayer.forward/backward x2 from pinned host tensors, graph plan rebuilt each step"}
 
-        # ---- CPU baseline: oracle port on a bounded sample
-        if not args.no_cpu:
-            s_ = CPU_SAMPLE
-            eps, dt, threads = cpu_layer_step(s_["N"], s_["R"], s_["E"], 2, 1)
-            line["cpu_baseline"] = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",
-                                    "sample": f"one layer fwd+bwd, N={s_['N']}, E={s_['E']}, R={s_['R']}, d={D}, {dt:.2f} s/step; x2 layers = same edges/s"}
+    if rank == 0 and "cpu" in sections:
+        s_ = CPU_SAMPLE
+        eps, dt, threads = cpu_layer_step(s_["N"], s_["R"], s_["E"], 2, 1)
+        line["cpu_baseline"] = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",
+                                "sample": f"one layer fwd+bwd, N={s_['N']}, E={s_['E']}, R={s_['R']}, d={D}, {dt:.2f} s/step; x2 layers = same edges/s"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# of this same workload (profiles/ncu_edge_kernels_r01.md); bytes.
+TRAFFIC_NCU = {"edge_fwd": 86.03e9, "edge_bwd_dst": 91.86e9, "edge_bwd_src": 55.31e9, "edge_bwd_rel": 49.88e9}
 
 
 def main():
@@ -322,7 +376,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N/E/B for debugging (bench numbers need 1.0)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sections", default="all", help="comma list of: " + ",".join(ALL_SECTIONS) + " (or 'all', or '' for headline only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

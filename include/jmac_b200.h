@@ -48,6 +48,12 @@ typedef struct jmac_plan jmac_plan;
 
 int jmac_plan_create(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, int64_t E,
                      int64_t N, int64_t n_rel, int chunk, void* stream, jmac_plan** out);
+/* Destination-sharded variant (multi-GPU): row indexes the N_dst nodes this shard aggregates into,
+ * col indexes a (gathered) source table of N_src rows.  P/agg/lse/G/dP are [N_dst,d]; Q/X and the
+ * source-pass outputs dXe/dQ are [N_src,d]. */
+int jmac_plan_create_bipartite(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type,
+                               int64_t E, int64_t N_dst, int64_t N_src, int64_t n_rel, int chunk,
+                               void* stream, jmac_plan** out);
 int jmac_plan_destroy(jmac_plan* plan);
 /* info[0..7] = E, N, n_rel, chunk, #dst work items, #src work items, #rel work items, max in-degree */
 int jmac_plan_info(const jmac_plan* plan, int64_t info[8]);

@@ -51,7 +51,7 @@ struct ItemList {
 }  // namespace jmac
 
 struct jmac_plan {
-    int64_t E = 0, N = 0, n_rel = 0;
+    int64_t E = 0, N = 0, N_src = 0, n_rel = 0;   // N = destination (aggregation) nodes, N_src = source table rows
     int chunk = 256;
     int max_deg = 0;
     // by destination (CSR)

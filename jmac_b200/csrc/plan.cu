@@ -50,12 +50,12 @@ static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
 }
 
 __global__ void make_keys_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
-                                 const int64_t* __restrict__ typ, int64_t E, int64_t N, int64_t n_rel, int tb,
+                                 const int64_t* __restrict__ typ, int64_t E, int64_t N, int64_t NS, int64_t n_rel, int tb,
                                  uint64_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bad) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= E) return;
     int64_t r = row[e], c = col[e], t = typ[e];
-    if (r < 0 || r >= N || c < 0 || c >= N || t < 0 || t >= n_rel) {
+    if (r < 0 || r >= N || c < 0 || c >= NS || t < 0 || t >= n_rel) {
         atomicOr(bad, 1);
         r = 0; t = 0;
     }
@@ -210,11 +210,11 @@ extern "C" int jmac_plan_destroy(jmac_plan* p) {
 }
 
 static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, cudaStream_t st) {
-    const int64_t E = p->E, N = p->N, R = p->n_rel;
+    const int64_t E = p->E, N = p->N, NS = p->N_src, R = p->n_rel;
     const size_t Eb = (size_t)(E > 0 ? E : 1);
-    const int tb = bits_for(R), nbits = bits_for(N);
+    const int tb = bits_for(R), nbits = bits_for(N), sbits = bits_for(NS);
     JMAC_CUDA(cudaMalloc(&p->rowptr, sizeof(int) * (size_t)(N + 1)));
-    JMAC_CUDA(cudaMalloc(&p->colptr, sizeof(int) * (size_t)(N + 1)));
+    JMAC_CUDA(cudaMalloc(&p->colptr, sizeof(int) * (size_t)(NS + 1)));
     JMAC_CUDA(cudaMalloc(&p->typptr, sizeof(int) * (size_t)(R + 1)));
     JMAC_CUDA(cudaMalloc(&p->sqrt_deg, sizeof(float) * (size_t)(N > 0 ? N : 1)));
     JMAC_CUDA(cudaMalloc(&p->csr_src, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csr_type, sizeof(int) * Eb));
@@ -238,7 +238,7 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         JMAC_CUDA(cudaMalloc(&k_in, sizeof(uint64_t) * Eb)); JMAC_CUDA(cudaMalloc(&k_out, sizeof(uint64_t) * Eb));
         JMAC_CUDA(cudaMalloc(&v_in, sizeof(int) * Eb));
         if (E > 0) {
-            make_keys_kernel<<<eblocks, threads, 0, st>>>(d_row, d_col, d_type, E, N, R, tb, k_in, v_in, flags);
+            make_keys_kernel<<<eblocks, threads, 0, st>>>(d_row, d_col, d_type, E, N, NS, R, tb, k_in, v_in, flags);
             JMAC_LAUNCH_CHECK();
         }
         JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
@@ -270,9 +270,9 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
     {
         int* sorted = nullptr;
         JMAC_CUDA(cudaMalloc(&sorted, sizeof(int) * Eb));
-        int rc = sort_by_int_key(p->csr_src, E, nbits, st, sorted, p->csc_pos);
+        int rc = sort_by_int_key(p->csr_src, E, sbits, st, sorted, p->csc_pos);
         if (rc) return rc;
-        build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)N, p->colptr);
+        build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)NS, p->colptr);
         JMAC_LAUNCH_CHECK();
         if (E > 0) { gather_int_kernel<<<eblocks, threads, 0, st>>>(p->csr_dst, p->csc_pos, E, p->csc_dst); JMAC_LAUNCH_CHECK(); }
         // ---- by relation type
@@ -287,30 +287,36 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
     cudaFree(flags);
     int rc = build_items(p->rowptr, (int)N, p->chunk, 1, st, &p->dst_items);
     if (rc) return rc;
-    rc = build_items(p->colptr, (int)N, p->chunk, 1, st, &p->src_items);
+    rc = build_items(p->colptr, (int)NS, p->chunk, 1, st, &p->src_items);
     if (rc) return rc;
     // relation pass: larger chunks (one CTA-wide warp loop per item), empty relations skipped
     rc = build_items(p->typptr, (int)R, p->chunk, 0, st, &p->typ_items);
     return rc;
 }
 
-extern "C" int jmac_plan_create(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, int64_t E, int64_t N,
-                                int64_t n_rel, int chunk, void* stream, jmac_plan** out) {
+extern "C" int jmac_plan_create_bipartite(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, int64_t E, int64_t N_dst,
+                                          int64_t N_src, int64_t n_rel, int chunk, void* stream, jmac_plan** out) {
     JMAC_ARG(out != nullptr);
     *out = nullptr;
     JMAC_ARG(E >= 0 && E < (int64_t(1) << 31) - 1);
-    JMAC_ARG(N > 0 && N < (int64_t(1) << 31) - 1);
+    JMAC_ARG(N_dst > 0 && N_dst < (int64_t(1) << 31) - 1);
+    JMAC_ARG(N_src > 0 && N_src < (int64_t(1) << 31) - 1);
     JMAC_ARG(n_rel > 0 && n_rel < (int64_t(1) << 24));
     JMAC_ARG(E == 0 || (d_row && d_col && d_type));
     JMAC_ARG(chunk >= 0 && chunk <= (1 << 20));
     jmac_plan* p = new (std::nothrow) jmac_plan();
     if (!p) return JMAC_ENOMEM;
-    p->E = E; p->N = N; p->n_rel = n_rel;
+    p->E = E; p->N = N_dst; p->N_src = N_src; p->n_rel = n_rel;
     p->chunk = chunk > 0 ? chunk : 256;
     int rc = plan_build(p, d_row, d_col, d_type, (cudaStream_t)stream);
     if (rc) { jmac_plan_destroy(p); return rc; }
     *out = p;
     return 0;
+}
+
+extern "C" int jmac_plan_create(const int64_t* d_row, const int64_t* d_col, const int64_t* d_type, int64_t E, int64_t N,
+                                int64_t n_rel, int chunk, void* stream, jmac_plan** out) {
+    return jmac_plan_create_bipartite(d_row, d_col, d_type, E, N, N, n_rel, chunk, stream, out);
 }
 
 extern "C" int jmac_plan_info(const jmac_plan* p, int64_t info[8]) {

@@ -103,6 +103,57 @@ def alignment_ranks(embed1, embed2, metric="inner", normalize=False, csls_k=0, d
     return pc["count"], pc["topi"][:, 0]
 
 
+def alignment_ranks_bf16(A, B, csls_k=10, group=None):
+    """Same three passes on already-converted bf16 tables ([n, dpad], gold column of row i = i).
+    With ``group`` the work is ROW-SHARDED by source entity across the ranks (every rank holds both
+    tables, 512 MB each at 1M x 256): pass A and C on this rank's rows of A, pass B on this rank's rows
+    of B, then an all-gather of r2 and a final all-gather of the per-row results (rows are disjoint,
+    so the "top-k merge" is a concatenation).  Returns (ranks[n1], top1[n1]) on every rank."""
+    import torch.distributed as dist
+    n1, n2 = A.shape[0], B.shape[0]
+    dev = A.device
+    world = dist.get_world_size(group) if group is not None else 1
+    rank = dist.get_rank(group) if group is not None else 0
+
+    def span(n):
+        per = (n + world - 1) // world
+        return min(rank * per, n), min((rank + 1) * per, n), per
+
+    a_lo, a_hi, a_per = span(n1)
+    b_lo, b_hi, b_per = span(n2)
+    A_loc, B_loc = A[a_lo:a_hi], B[b_lo:b_hi]
+    gold_col = torch.arange(a_lo, a_hi, dtype=torch.int32, device=dev)
+    if csls_k > 0:
+        pa = sim_topk(A_loc, B, csls_k, gold_col=gold_col, want_diag=True)
+        pb = sim_topk(B_loc, A, csls_k)
+        r1 = pa["topv"].mean(1).contiguous()
+        r2_loc = pb["topv"].mean(1).contiguous()
+        if world > 1:
+            buf = torch.zeros(b_per, dtype=torch.float32, device=dev)
+            buf[: r2_loc.numel()] = r2_loc
+            r2_all = torch.empty(world * b_per, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(r2_all, buf, group=group)
+            r2 = r2_all[:n2].contiguous()
+        else:
+            r2 = r2_loc
+        alpha = 2.0
+    else:
+        pa = sim_topk(A_loc, B, 0, gold_col=gold_col, want_diag=True)
+        r1 = r2 = None
+        alpha = 1.0
+    gold_val = csls_gold(alpha, pa["diag"], r1, r2, gold_col if r2 is not None else None)
+    pc = sim_topk(A_loc, B, 1, alpha=alpha, r1=r1, r2=r2, gold_val=gold_val, want_count=True)
+    ranks, top1 = pc["count"], pc["topi"][:, 0].contiguous()
+    if world > 1:
+        pack = torch.zeros(a_per, 2, dtype=torch.int32, device=dev)
+        pack[: ranks.numel(), 0] = ranks
+        pack[: ranks.numel(), 1] = top1
+        allp = torch.empty(world * a_per, 2, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, pack, group=group)
+        ranks, top1 = allp[:n1, 0].contiguous(), allp[:n1, 1].contiguous()
+    return ranks, top1
+
+
 def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csls_k, accurate, simi_matrix=None, return_simi=False,
                      logger=None):
     """modules/finding/alignment.py:10-69 -- returns (top_k, hits% rounded to 3 dp, mr, mrr)."""

@@ -50,7 +50,7 @@ def as_index(x, device) -> torch.Tensor:
 class GraphPlan:
     """Owns a ``jmac_plan`` (CSR-by-destination + by-source + by-relation orderings)."""
 
-    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int, chunk: int = 0):
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int, chunk: int = 0, n_src: int = None):
         _need_cuda(edge_index, edge_type)
         lib = _lib.load()
         ei = edge_index.to(torch.int64).contiguous()
@@ -58,11 +58,12 @@ class GraphPlan:
         if ei.dim() != 2 or ei.shape[0] != 2 or et.shape[0] != ei.shape[1]:
             raise ValueError("edge_index must be [2,E] and edge_type [E]")
         self.E, self.N, self.n_rel = int(ei.shape[1]), int(num_ent), int(n_rel)
+        self.N_src = int(n_src) if n_src is not None else self.N      # != N only for destination-sharded plans
         self.device = ei.device
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            check(lib.jmac_plan_create(ptr(ei[0]), ptr(ei[1]), ptr(et), self.E, self.N, self.n_rel, int(chunk), stream_ptr(),
-                                       ctypes.byref(handle)), "jmac_plan_create")
+            check(lib.jmac_plan_create_bipartite(ptr(ei[0]), ptr(ei[1]), ptr(et), self.E, self.N, self.N_src, self.n_rel, int(chunk),
+                                                 stream_ptr(), ctypes.byref(handle)), "jmac_plan_create")
         self._h = handle
         info = (ctypes.c_int64 * 8)()
         check(lib.jmac_plan_info(self._h, info), "jmac_plan_info")
@@ -130,10 +131,10 @@ class EdgePhaseFn(torch.autograd.Function):
         _need_cuda(P, Q, X, S, Rp, a_att)
         lib = _lib.load()
         P, Q, X, S, Rp, a = (_f32c(t) for t in (P, Q, X, S, Rp, a_att.reshape(-1)))
-        N, d = X.shape
-        if N != plan.N or S.shape[0] != plan.n_rel or Rp.shape[0] != plan.n_rel:
+        N, d = P.shape
+        if N != plan.N or X.shape[0] != plan.N_src or Q.shape[0] != plan.N_src or S.shape[0] != plan.n_rel or Rp.shape[0] != plan.n_rel:
             raise ValueError("table sizes do not match the graph plan")
-        agg = torch.empty_like(X)
+        agg = torch.empty_like(P)
         lse = torch.empty(N, dtype=torch.float32, device=X.device)
         with torch.cuda.device(X.device):
             check(lib.jmac_edge_fwd(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
@@ -148,10 +149,10 @@ class EdgePhaseFn(torch.autograd.Function):
         lib = _lib.load()
         P, Q, X, S, Rp, a, agg, lse = ctx.saved_tensors
         plan, slope = ctx.plan, ctx.slope
-        N, d = X.shape
+        d = X.shape[1]
         G = _f32c(g)
         dev = X.device
-        dP = torch.empty_like(X)
+        dP = torch.empty_like(P)
         dXe = torch.empty_like(X)
         dQ = torch.empty_like(X)
         dRp = torch.empty_like(Rp)
