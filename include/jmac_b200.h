@@ -183,6 +183,17 @@ int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, 
                   float alpha, const float* r1, const float* r2, const int32_t* gold_col,
                   const float* gold_val, int32_t* gold_cnt, float* diag, float* topv,
                   int32_t* topi, void* stream);
+/* Softmax statistics of x_ij = alpha * S_ij per row i, never materialising the matrix
+ * (compute_alignment_quality, train.py:231-259: softmax(simi * 20), its entropy, its row max/argmax).
+ * Rows with row_mask[i] != 0 and columns with col_mask[j] != 0 take x = masked_value instead
+ * (train.py:254-255 sets them to -1, i.e. masked_value = -alpha).  col_mask follows the r2 rules
+ * (padded to a multiple of 128, 16-byte aligned); either mask may be NULL.  Outputs per row:
+ *   out_max = max_j x, out_arg = first argmax, out_Z = sum_j e^(x - max), out_W = sum_j e^(x-max) (x-max)
+ * so that  max probability = 1/Z  and  entropy = log Z - W/Z. */
+int jmac_sim_softmax_stats(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, int dpad,
+                           float alpha, const float* row_mask, const float* col_mask,
+                           float masked_value, float* out_max, int32_t* out_arg, float* out_Z,
+                           float* out_W, void* stream);
 /* out[i] = (alpha * diag[i] - r1[i]) - r2[gold_col[i]], with the exact operation order of the
  * epilogue above, so that the gold entry never counts as greater than itself. */
 int jmac_csls_gold(float alpha, const float* diag, const float* r1, const float* r2,

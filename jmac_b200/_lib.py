@@ -40,6 +40,7 @@ _SIGNATURES = {
     "jmac_to_bf16_rows": (c_int, [P, c_int, P, c_int64, c_int, P, c_int, P]),
     "jmac_sim_topk": (c_int, [P, P, c_int64, c_int64, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P]),
     "jmac_csls_gold": (c_int, [c_float, P, P, P, P, c_int64, P, P]),
+    "jmac_sim_softmax_stats": (c_int, [P, P, c_int64, c_int64, c_int, c_float, P, P, c_float, P, P, P, P, P]),
     "jmac_l1_rank": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int, P, P, P, P]),
 }
 

@@ -44,6 +44,10 @@ struct SimParams {
     float* diag;
     float* topv;
     int* topi;
+    // softmax-statistics mode (STATS): r1 = row mask, r2 = column mask (non-zero = masked)
+    float masked;
+    float *st_m, *st_Z, *st_W;
+    int* st_arg;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -134,7 +138,7 @@ struct TopK {
     }
 };
 
-template <int KMAX, bool CSLS>
+template <int KMAX, bool CSLS, bool STATS>
 __global__ void __launch_bounds__(SIM_THREADS, 1)
 sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, SimParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -246,6 +250,8 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int gcol = (p.diag && rvalid) ? p.gold_col[row] : -1;
             int cnt = 0;
             float dg = 0.f;
+            float st_m = -INFINITY, st_Z = 0.f, st_W = 0.f;
+            int st_arg = 0;
             for (int ct = 0; ct < n_ct; ++ct, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                 const uint32_t rs = tcount & 1, rph = (tcount >> 1) & 1;
@@ -269,6 +275,45 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             if (col0 + j == gcol) dg = __uint_as_float(rw[j]);
                     }
                     float v[32];
+                    if (STATS) {
+                        // softmax statistics of x = alpha*S with masked rows / columns forced to p.masked
+                        // (compute_alignment_quality, train.py:231-259): running max m, argmax, Z = sum e^(x-m),
+                        // W = sum e^(x-m) (x-m).  Entropy = log Z - W/Z, max probability = 1/Z.
+                        bool ok[32];
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            float4 cm = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (CSLS) cm = *reinterpret_cast<const float4*>(r2t + c * 32 + 4 * j4);
+                            const float cmv[4] = {cm.x, cm.y, cm.z, cm.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int j = 4 * j4 + q;
+                                const bool masked = (r1 != 0.f) || (cmv[q] != 0.f);
+                                v[j] = masked ? p.masked : p.alpha * __uint_as_float(rw[j]);
+                                ok[j] = !ragged || (col0 + j < p.n2);
+                            }
+                        }
+                        float cmax = -INFINITY;
+                        int carg = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (ok[j] && v[j] > cmax) { cmax = v[j]; carg = j; }
+                        if (cmax > st_m) {
+                            const float sc = __expf(st_m - cmax);                   // 0 on the first chunk (st_m = -inf)
+                            st_W = st_Z > 0.f ? (st_W + (st_m - cmax) * st_Z) * sc : 0.f;
+                            st_Z *= sc;
+                            st_m = cmax;
+                            st_arg = col0 + carg;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float t = ok[j] ? v[j] - st_m : 0.f;
+                            const float e = ok[j] ? __expf(t) : 0.f;
+                            st_Z += e;
+                            st_W = fmaf(e, t, st_W);
+                        }
+                        continue;
+                    }
                     if (CSLS) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
@@ -326,6 +371,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 if (want_cnt) p.gold_cnt[row] = cnt;
                 if (p.diag) p.diag[row] = dg;
+                if (STATS) { p.st_m[row] = st_m; p.st_Z[row] = st_Z; p.st_W[row] = st_W; p.st_arg[row] = st_arg; }
             }
         }
     }
@@ -433,18 +479,49 @@ extern "C" int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, i
     SimParams p;
     p.n1 = (int)n1; p.n2 = (int)n2; p.nks = dpad / SIM_BK; p.k = k; p.alpha = alpha; p.r1 = r1; p.r2 = r2;
     p.gold_col = gold_col; p.gold_val = gold_val; p.gold_cnt = gold_cnt; p.diag = diag; p.topv = topv; p.topi = topi;
+    p.masked = 0.f; p.st_m = p.st_Z = p.st_W = nullptr; p.st_arg = nullptr;
     const int n_rb = (int)((n1 + SIM_BM - 1) / SIM_BM);
     const int grid = n_rb < sm_count() ? n_rb : sm_count();
     cudaStream_t st = (cudaStream_t)stream;
 #define JMAC_SIM_LAUNCH(KM, CS)                                                                                          \
     do {                                                                                                                 \
-        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<KM, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM)); \
-        sim_topk_kernel<KM, CS><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);                                    \
+        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<KM, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM)); \
+        sim_topk_kernel<KM, CS, false><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);                                    \
     } while (0)
     if (k <= 1)       { if (r2) JMAC_SIM_LAUNCH(1, true);  else JMAC_SIM_LAUNCH(1, false); }
     else if (k <= 16) { if (r2) JMAC_SIM_LAUNCH(16, true); else JMAC_SIM_LAUNCH(16, false); }
     else              { if (r2) JMAC_SIM_LAUNCH(32, true); else JMAC_SIM_LAUNCH(32, false); }
 #undef JMAC_SIM_LAUNCH
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int jmac_sim_softmax_stats(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, int dpad, float alpha,
+                                      const float* row_mask, const float* col_mask, float masked_value, float* out_max, int32_t* out_arg,
+                                      float* out_Z, float* out_W, void* stream) {
+    JMAC_ARG(A && B && out_max && out_arg && out_Z && out_W);
+    JMAC_ARG(n1 > 0 && n2 > 0 && n1 < (int64_t(1) << 31) && n2 < (int64_t(1) << 31));
+    JMAC_ARG(dpad >= 64 && dpad <= SIM_MAX_KS * SIM_BK && (dpad % 64) == 0);
+    JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && (col_mask == nullptr || ((uintptr_t)col_mask % 16) == 0));
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, A, n1, dpad, SIM_BM);
+    if (rc) return rc;
+    rc = make_map(&map_b, B, n2, dpad, SIM_BN);
+    if (rc) return rc;
+    SimParams p;
+    p.n1 = (int)n1; p.n2 = (int)n2; p.nks = dpad / SIM_BK; p.k = 0; p.alpha = alpha; p.r1 = row_mask; p.r2 = col_mask;
+    p.gold_col = nullptr; p.gold_val = nullptr; p.gold_cnt = nullptr; p.diag = nullptr; p.topv = nullptr; p.topi = nullptr;
+    p.masked = masked_value; p.st_m = out_max; p.st_Z = out_Z; p.st_W = out_W; p.st_arg = out_arg;
+    const int n_rb = (int)((n1 + SIM_BM - 1) / SIM_BM);
+    const int grid = n_rb < sm_count() ? n_rb : sm_count();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (col_mask) {
+        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM));
+        sim_topk_kernel<1, true, true><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);
+    } else {
+        JMAC_CUDA(cudaFuncSetAttribute(sim_topk_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM));
+        sim_topk_kernel<1, false, true><<<grid, SIM_THREADS, SIM_SMEM, st>>>(map_a, map_b, p);
+    }
     JMAC_LAUNCH_CHECK();
     return 0;
 }

@@ -210,6 +210,84 @@ def get_neg(ILL, emb_src, emb_dst, k):
     return out
 
 
+# ---- alignment quality / seed enlargement (train.py:231-259, 163-169) ---------------------------
+def softmax_stats(A, B, alpha, row_mask=None, col_mask=None, masked_value=None):
+    """Per-row softmax statistics of alpha * A.B^T (see jmac_sim_softmax_stats): dict(max, arg, Z, W)."""
+    lib = _lib.load()
+    n1, n2, dpad = A.shape[0], B.shape[0], A.shape[1]
+    dev = A.device
+    if col_mask is not None:
+        n2p = (n2 + 127) // 128 * 128
+        cm = torch.zeros(n2p, dtype=torch.float32, device=dev)
+        cm[:n2] = col_mask.to(dev, torch.float32)
+        col_mask = cm
+    if row_mask is not None:
+        row_mask = row_mask.to(dev, torch.float32).contiguous()
+    out = {"max": torch.empty(n1, dtype=torch.float32, device=dev), "arg": torch.empty(n1, dtype=torch.int32, device=dev),
+           "Z": torch.empty(n1, dtype=torch.float32, device=dev), "W": torch.empty(n1, dtype=torch.float32, device=dev)}
+    with torch.cuda.device(dev):
+        check(lib.jmac_sim_softmax_stats(ptr(A), ptr(B), n1, n2, dpad, float(alpha), ptr(row_mask), ptr(col_mask),
+                                         float(-alpha if masked_value is None else masked_value), ptr(out["max"]), ptr(out["arg"]),
+                                         ptr(out["Z"]), ptr(out["W"]), stream_ptr()), "jmac_sim_softmax_stats")
+    return out
+
+
+class SoftmaxRows:
+    """What train.py:165-168 needs from the dense ``softmax_simi`` matrix, without the matrix:
+    ``simi.max(dim=1)`` -> (row max probability, row argmax) and ``simi[rows].max(dim=1)`` likewise.
+    (``torch.multinomial`` on the row-max vector stays in torch for RNG parity.)"""
+
+    def __init__(self, maxp: torch.Tensor, arg: torch.Tensor, shape):
+        self._maxp, self._arg, self.shape = maxp, arg, tuple(shape)
+
+    def max(self, dim=1):
+        if dim not in (1, -1):
+            raise NotImplementedError("only row-wise max is available without materialising the matrix")
+        return self._maxp, self._arg
+
+    def __getitem__(self, rows):
+        idx = as_index(rows, self._maxp.device) if not isinstance(rows, slice) else rows
+        return SoftmaxRows(self._maxp[idx], self._arg[idx], (self._maxp[idx].shape[0], self.shape[1]))
+
+    def __len__(self):
+        return self.shape[0]
+
+
+def compute_alignment_quality(embedding1, embedding2, list1, list2, scale=20.0):
+    """train.py:231-259.  Returns (entropy, softmax_simi, softmax_simi2) where the two "matrices" are
+    ``SoftmaxRows`` views (row max / argmax only) -- exactly what seed enlargement consumes
+    (train.py:165-168) -- and ``entropy`` is a 0-dim CPU tensor as in the reference.
+    Streaming: four passes of the similarity kernel in softmax-statistics mode; the reference's
+    O(N*L) Python ``not in list`` scans and dense N1 x N2 CPU softmaxes are gone."""
+    e1, e2 = _dev_f32(embedding1), _dev_f32(embedding2)
+    dev = e1.device
+    n1, n2 = e1.shape[0], e2.shape[0]
+    l1, l2 = as_index(list1, dev), as_index(list2, dev)
+    # (1) entropy over the sub-matrix of the valid alignment entities, both directions
+    A_sub, B_sub = to_bf16_rows(e1, idx=l1), to_bf16_rows(e2, idx=l2)
+    s12 = softmax_stats(A_sub, B_sub, scale)
+    s21 = softmax_stats(B_sub, A_sub, scale)
+    ent = (torch.log(s12["Z"]) - s12["W"] / s12["Z"]).mean() + (torch.log(s21["Z"]) - s21["W"] / s21["Z"]).mean()
+    # (2) full matrix with rows not in list1 / columns not in list2 set to -1 (train.py:252-255)
+    A, B = to_bf16_rows(e1), to_bf16_rows(e2)
+    m1 = torch.ones(n1, dtype=torch.float32, device=dev)
+    m1[l1] = 0
+    m2 = torch.ones(n2, dtype=torch.float32, device=dev)
+    m2[l2] = 0
+    f12 = softmax_stats(A, B, scale, row_mask=m1, col_mask=m2)
+    f21 = softmax_stats(B, A, scale, row_mask=m2, col_mask=m1)
+    out_cpu = torch.is_tensor(embedding1) and not embedding1.is_cuda
+
+    def view(f, shape):
+        maxp, arg = 1.0 / f["Z"], f["arg"].to(torch.int64)
+        if out_cpu:
+            maxp, arg = maxp.cpu(), arg.cpu()
+        return SoftmaxRows(maxp, arg, shape)
+
+    ent = ent.cpu() if out_cpu else ent
+    return ent, view(f12, (n1, n2)), view(f21, (n2, n1))
+
+
 # ---- dense convenience API (small inputs only; not the hot path) ---------------------------------
 def sim(embed1, embed2, metric='inner', normalize=False, csls_k=0):
     """modules/finding/similarity.py:13-55 for callers that really want the dense matrix (numpy

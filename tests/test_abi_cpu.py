@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
     lib = ctypes.CDLL(_lib.LIB_PATH)
     syms = header_symbols()
-    assert len(syms) >= 26
+    assert len(syms) >= 27
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == syms, "ctypes signature table and header disagree"

@@ -116,3 +116,35 @@ def test_dense_sim_api(golden):
     np.testing.assert_allclose(F.sim(g["e1"], g["e2"], "cosine", False, 0), g["sim_cos"], atol=2e-6)
     np.testing.assert_allclose(F.sim(g["e1"], g["e2"], "cosine", False, 10), g["sim_cos_csls10"], atol=5e-6)
     np.testing.assert_allclose(F.csls_sim(g["sim_cos"], 10), g["sim_cos_csls10"], atol=5e-6)
+
+
+@pytest.mark.parametrize("n1,n2,d,L", [(300, 260, 64, 90), (1000, 1100, 256, 400)])
+def test_compute_alignment_quality_matches_oracle_on_bf16_inputs(n1, n2, d, L):
+    """train.py:231-259 and its consumer (train.py:165-168) without the dense matrices."""
+    from jmac_b200 import finding as F
+    e1, e2 = planted(n1, n2, d, 77, noise=1.0)
+    rng = np.random.default_rng(5)
+    l1 = rng.permutation(min(n1, n2))[:L]
+    l2 = l1.copy()                                  # aligned test pairs share the planted index
+    t1, t2 = torch.from_numpy(e1), torch.from_numpy(e2)
+    ent, simi, simi2 = F.compute_alignment_quality(t1, t2, l1.tolist(), l2.tolist())
+    a, b = torch.from_numpy(bf16_round(e1)).double(), torch.from_numpy(bf16_round(e2)).double()
+    oent, o1, o2 = O.compute_alignment_quality(a, b, l1, l2)
+    np.testing.assert_allclose(float(ent), float(oent), rtol=2e-4)
+    assert not ent.is_cuda and ent.dim() == 0
+    for view, dense in ((simi, o1), (simi2, o2)):
+        mv, mi = view.max(dim=1)
+        ov, oi = dense.max(1)
+        np.testing.assert_allclose(mv.numpy(), ov.numpy(), rtol=2e-4, atol=1e-7)
+        sd = torch.sort(dense, dim=1, descending=True)[0]
+        clear = ((sd[:, 0] - sd[:, 1]) > 1e-4 * sd[:, 0]).numpy()          # documented ties (incl. fully masked rows: uniform)
+        assert np.array_equal(mi.numpy()[clear], oi.numpy()[clear])
+        assert len(view) == dense.shape[0] and view.shape == tuple(dense.shape)
+    # the reference's consumer code runs unchanged on the view (train.py:165-168)
+    torch.manual_seed(0)
+    max_values = simi.max(dim=1)[0]
+    src_nodes = max_values.multinomial(20, replacement=False).tolist()
+    rows = simi[src_nodes]
+    dst_nodes = rows.max(dim=1)[1].tolist()
+    assert len(dst_nodes) == 20 and all(0 <= x < n2 for x in dst_nodes)
+    assert dst_nodes == simi.max(dim=1)[1][src_nodes].tolist()
