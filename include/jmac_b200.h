@@ -119,6 +119,16 @@ int jmac_bn_tanh_bwd_apply(const float* gout, const float* out, const float* pre
                            float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Node-level dense product with fp32 accuracy on the tensor cores (3xTF32 split, tcgen05):
+ *   C[M,N] = A[M,K] . B[N,K]^T,  B given pre-split: B_hi = B with the low 13 mantissa bits cleared,
+ *   B_lo = B - B_hi.  N % 32 == 0, N <= 256, K % 16 == 0; lda/ldb/ldc in elements (multiples of 4).
+ * Replaces the fp32 library GEMMs of the hoisted per-edge products of src/jmac_model.py:75-76,88
+ * (P = X W_top, Q = X W_bot, pre = T W_g) and their input-gradient transposes.
+ * ------------------------------------------------------------------------------------------ */
+int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                     float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Completion scorer: TransE-L1 margin loss of JMAC.completion_loss (src/jmac_model.py:345-374)
  * on the reference's exact batch layout (train.py:347-352): M = (1+K)*B triples, positives are the
  * first B, the negative at flat position B + k*B + b is compared with positive b.

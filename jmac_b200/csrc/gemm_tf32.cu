@@ -1,0 +1,292 @@
+// Node-level dense products of the GNN layer at tensor-core speed with fp32 accuracy:
+//     C[M,N] = A[M,K] . B[N,K]^T        (fp32 in / out, N <= 256, K % 16 == 0)
+// computed as three tcgen05 kind::tf32 products (3xTF32 split, error ~2^-21):
+//     A = A_hi + A_lo,  B = B_hi + B_lo  (hi = top 19 bits),   C ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.
+// Replaces the fp32 SIMT library GEMMs behind torch.mm for  P = X W_top, Q = X W_bot,
+// pre = T W_g  (src/jmac_model.py:75-76,88 hoisted to node level) and their input-gradient transposes;
+// a TF32-only product would miss the 1e-4 parity bar, a SIMT product is 5x slower.
+//
+// CTA = 320 threads, persistent over 256-row blocks of A:
+//   warp 0   TMA producer: per 16-wide K slice one box of A (256 rows x 64 B) and the pre-split
+//            B_hi / B_lo slices (N rows x 64 B each), SWIZZLE_64B, 3-stage ring;
+//   warps 2-9 split A in shared memory (hi written back in place, lo to a second buffer; elementwise,
+//            so the swizzled layout is preserved), fence.proxy.async, then act as the epilogue;
+//   warp 1   single-thread tcgen05.mma issuer: 2 row halves x 2 K-steps x 3 products per slice into two
+//            128 x N fp32 accumulators in TMEM (512 columns);
+//   epilogue tcgen05.ld 32x32b.x32 -> registers -> 128-bit global stores (each thread owns one row).
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace jmac {
+namespace {
+
+constexpr int G_BM = 256, G_BK = 16, G_NS = 3, G_THREADS = 320;
+constexpr int G_A_BYTES = G_BM * G_BK * 4;          // 16 KB (raw -> hi in place)
+constexpr int G_B_BYTES = 256 * G_BK * 4;           // 16 KB per hi / lo slice (N <= 256)
+constexpr int G_STAGE = 2 * G_A_BYTES + 2 * G_B_BYTES;   // A_hi, A_lo, B_hi, B_lo = 64 KB
+constexpr int G_SMEM = G_NS * G_STAGE + 1024 + 256;
+static_assert(G_SMEM <= 232448, "shared memory budget");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// round-to-nearest (ties away) to TF32: |x - hi| <= 2^-11 |x|, so the dropped lo.lo term is <= 2^-22
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r & 0xFFFFE000u);
+}
+
+// K-major SWIZZLE_64B descriptor: rows of 16 fp32 (64 B), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;              // SWIZZLE_64B
+    return d;
+}
+
+struct GemmParams {
+    int M, N, nkb;      // nkb = K / 16
+    float* C;
+    int ldc;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                   const __grid_constant__ CUtensorMap map_blo, GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + G_NS * G_STAGE;
+    // barriers: tma_full[NS], xf_full[NS], empty[NS], acc_full, acc_empty, tmem slot
+    const uint32_t tma_full0 = bars, xf_full0 = bars + 8 * G_NS, empty0 = bars + 16 * G_NS, acc_full = bars + 24 * G_NS,
+                   acc_empty = acc_full + 8, tmem_slot = acc_empty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mb = (p.M + G_BM - 1) / G_BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_NS; ++s) { mbar_init(tma_full0 + 8 * s, 1); mbar_init(xf_full0 + 8 * s, 8); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const uint32_t b_bytes = (uint32_t)p.N * G_BK * 4;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int mb = blockIdx.x; mb < n_mb; mb += gridDim.x) {
+                for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                    const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
+                    const uint32_t st = base + s * G_STAGE;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    mbar_expect_tx(tma_full0 + 8 * s, G_A_BYTES + 2 * b_bytes);
+                    tma_load_2d(st, &map_a, tma_full0 + 8 * s, kb * G_BK, mb * G_BM);
+                    tma_load_2d(st + 2 * G_A_BYTES, &map_bhi, tma_full0 + 8 * s, kb * G_BK, 0);
+                    tma_load_2d(st + 2 * G_A_BYTES + G_B_BYTES, &map_blo, tma_full0 + 8 * s, kb * G_BK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // kind::tf32: A = B = TF32 (2), D = F32 (1), K-major both, M = 128, N = p.N
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t it = 0, tcount = 0;
+            for (int mb = blockIdx.x; mb < n_mb; mb += gridDim.x, ++tcount) {
+                mbar_wait(acc_empty, (tcount & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                    const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
+                    const uint32_t st = base + s * G_STAGE;
+                    mbar_wait(xf_full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint64_t bhi = umma_desc_sw64(st + 2 * G_A_BYTES), blo = umma_desc_sw64(st + 2 * G_A_BYTES + G_B_BYTES);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint64_t ahi = umma_desc_sw64(st + half * (128 * G_BK * 4));
+                        const uint64_t alo = umma_desc_sw64(st + G_A_BYTES + half * (128 * G_BK * 4));
+                        const uint32_t d_tmem = tmem_base + half * 256;
+#pragma unroll
+                        for (int kk = 0; kk < G_BK / 8; ++kk) {
+                            const uint64_t o = (uint64_t)(kk * 2);          // +32 B per K step of 8 tf32
+                            tc_mma_tf32(d_tmem, ahi + o, bhi + o, idesc, (kb | kk) != 0 ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, alo + o, bhi + o, idesc, 1u);
+                            tc_mma_tf32(d_tmem, ahi + o, blo + o, idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty0 + 8 * s);
+                }
+                tc_commit(acc_full);
+            }
+        }
+    } else {
+        const int w = warp - 2;                       // 0..7
+        const int quarter = warp & 3, half = w >> 2;
+        uint32_t it = 0, tcount = 0;
+        for (int mb = blockIdx.x; mb < n_mb; mb += gridDim.x, ++tcount) {
+            // ---- split the A slices of this block as they land
+            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
+                mbar_wait(tma_full0 + 8 * s, ph);
+                float4* hi = reinterpret_cast<float4*>(gbase + s * G_STAGE);
+                float4* lo = reinterpret_cast<float4*>(gbase + s * G_STAGE + G_A_BYTES);
+#pragma unroll
+                for (int r = 0; r < G_A_BYTES / 16 / 256; ++r) {      // 1024 float4 / 256 threads
+                    const int i = r * 256 + w * 32 + lane;
+                    const float4 x = hi[i];
+                    float4 h, l;
+                    h.x = tf32_rna(x.x); l.x = x.x - h.x;        // hi exactly representable in TF32, lo exact in fp32
+                    h.y = tf32_rna(x.y); l.y = x.y - h.y;
+                    h.z = tf32_rna(x.z); l.z = x.z - h.z;
+                    h.w = tf32_rna(x.w); l.w = x.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_full0 + 8 * s);
+            }
+            // ---- epilogue: TMEM -> registers -> global
+            mbar_wait(acc_full, tcount & 1);
+            tc_fence_after();
+            const int row = mb * G_BM + half * 128 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 256;
+            float* crow = p.C + (size_t)row * p.ldc;
+            uint32_t raw[2][32];
+            const int nchunk = p.N / 32;               // N % 32 == 0 enforced by the host
+            tc_ld32_issue(taddr, raw[0]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < nchunk) {
+                    tc_ld_wait();
+                    if (c + 1 < nchunk) tc_ld32_issue(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
+                    if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 v = make_float4(__uint_as_float(raw[c & 1][4 * j]), __uint_as_float(raw[c & 1][4 * j + 1]),
+                                                   __uint_as_float(raw[c & 1][4 * j + 2]), __uint_as_float(raw[c & 1][4 * j + 3]));
+                            reinterpret_cast<float4*>(crow + c * 32)[j] = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult r;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)q;
+    }
+    return fn;
+}
+
+int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int K, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return JMAC_EINVAL; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r); return JMAC_EINVAL; }
+    return 0;
+}
+
+}  // namespace
+}  // namespace jmac
+
+using namespace jmac;
+
+extern "C" int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C, int64_t ldc,
+                                int64_t M, int N, int K, void* stream) {
+    JMAC_ARG(A && B_hi && B_lo && C && M > 0 && M < (int64_t(1) << 31));
+    JMAC_ARG(N >= 32 && N <= 256 && (N % 32) == 0 && K >= 16 && (K % 16) == 0);
+    JMAC_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0);
+    JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)B_lo % 16) == 0 && ((uintptr_t)C % 16) == 0);
+    CUtensorMap map_a, map_bhi, map_blo;
+    int rc = make_map_f32(&map_a, A, M, K, lda, G_BM);
+    if (rc) return rc;
+    rc = make_map_f32(&map_bhi, B_hi, N, K, ldb, N);
+    if (rc) return rc;
+    rc = make_map_f32(&map_blo, B_lo, N, K, ldb, N);
+    if (rc) return rc;
+    GemmParams p;
+    p.M = (int)M; p.N = N; p.nkb = K / G_BK; p.C = C; p.ldc = (int)ldc;
+    const int n_mb = (int)((M + G_BM - 1) / G_BM);
+    const int grid = n_mb < sm_count() ? n_mb : sm_count();
+    JMAC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    gemm_tf32x3_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(map_a, map_bhi, map_blo, p);
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}

@@ -147,13 +147,14 @@ def sharded_layer_forward(layer, x_loc, rel_emb, shard: Shard, plan, group, ops=
         raise NotImplementedError
     Rp = layer.relation_transform(rel_emb)
     x_loc = x_loc.contiguous()
-    P = torch.mm(x_loc, layer.w_att[:d])
-    Q_loc = torch.mm(x_loc, layer.w_att[d:])
+    mm = getattr(ops, "node_mm", torch.mm)
+    P = mm(x_loc, layer.w_att[:d])
+    Q_loc = mm(x_loc, layer.w_att[d:])
     S = torch.mm(Rp, layer.w_att[d:])
     Qf = GatherRowsFn.apply(Q_loc, shard, group)          # halo exchange (full tables in this version)
     Xf = GatherRowsFn.apply(x_loc, shard, group)
     agg = ops.edge_phase(plan, P, Qf, Xf, S, Rp, layer.a_att, layer.leaky_slope)
-    pre = torch.mm(agg + x_loc - Rp[-1], layer.gcn_weight * 0.5)
+    pre = mm(agg + x_loc - Rp[-1], layer.gcn_weight * 0.5)
     training = layer.training or not layer.bn.track_running_stats
     if layer.training and layer.bn.track_running_stats:
         layer.bn.num_batches_tracked += 1

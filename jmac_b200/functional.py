@@ -174,6 +174,62 @@ def edge_phase(plan, P, Q, X, S, Rp, a_att, slope):
 
 
 # ----------------------------------------------------------------------------------------------
+# node-level dense products (3xTF32 on tcgen05, fp32-accurate)
+# ----------------------------------------------------------------------------------------------
+def _split_tf32(w_nk: torch.Tensor):
+    """hi = w rounded to nearest TF32 (ties away, like cvt.rna.tf32.f32; low 13 mantissa bits zero),
+    lo = w - hi (exact in fp32)."""
+    hi = ((w_nk.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return hi, w_nk - hi
+
+
+def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ B_nk[N,K]^T through jmac_gemm_tf32x3 (raises on unsupported shapes)."""
+    lib = _lib.load()
+    _need_cuda(A, B_nk)
+    A, B_nk = _f32c(A), _f32c(B_nk)
+    M, K = A.shape
+    N = B_nk.shape[0]
+    hi, lo = _split_tf32(B_nk)
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.jmac_gemm_tf32x3(ptr(A), K, ptr(hi), ptr(lo), K, ptr(C), N, M, N, K, stream_ptr()), "jmac_gemm_tf32x3")
+    return C
+
+
+def _tc_eligible(M, K, N) -> bool:
+    return M >= 4096 and N % 32 == 0 and 32 <= N <= 256 and K % 16 == 0 and K >= 16
+
+
+class NodeMatmulFn(torch.autograd.Function):
+    """Y = X @ W for a tall node table X[M,K] and a small weight W[K,N]."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        ctx.save_for_backward(X, W)
+        return gemm_nt(X, W.t().contiguous())
+
+    @staticmethod
+    def backward(ctx, G):
+        X, W = ctx.saved_tensors
+        G = _f32c(G)
+        dX = dW = None
+        if ctx.needs_input_grad[0]:
+            M, N = G.shape
+            dX = gemm_nt(G, W.contiguous()) if _tc_eligible(M, N, W.shape[0]) else G @ W.t()
+        if ctx.needs_input_grad[1]:
+            dW = X.t() @ G          # K x N reduction over all nodes: library GEMM for now (DESIGN.md section 7)
+        return dX, dW
+
+
+def node_mm(X: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """``torch.mm(X, W)`` semantics; large node tables go through the 3xTF32 tensor-core kernel."""
+    if X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and _tc_eligible(X.shape[0], X.shape[1], W.shape[1]):
+        return NodeMatmulFn.apply(X, W)
+    return torch.mm(X, W)
+
+
+# ----------------------------------------------------------------------------------------------
 # BatchNorm1d(over nodes) + tanh
 # ----------------------------------------------------------------------------------------------
 class BNTanhFn(torch.autograd.Function):

@@ -78,11 +78,11 @@ class RelationAwareLayer(nn.Module):
         Rp = self.relation_transform(rel_emb)                                    # [nr+1, d]; row nr = self loop
         plan = JF.get_plan(edge_index, edge_type, num_ent, Rp.size(0))
         X = ent_emb.contiguous()
-        P = torch.mm(X, self.w_att[:d])
-        Q = torch.mm(X, self.w_att[d:])
+        P = JF.node_mm(X, self.w_att[:d])           # node tables: 3xTF32 tcgen05 GEMM (fp32-accurate), small ones: library
+        Q = JF.node_mm(X, self.w_att[d:])
         S = torch.mm(Rp, self.w_att[d:])
         agg = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope)   # neighbours, pre-GEMM
-        pre = torch.mm(agg + X - Rp[-1], self.gcn_weight * 0.5)                  # (neigh + self)/2, :49-52
+        pre = JF.node_mm(agg + X - Rp[-1], self.gcn_weight * 0.5)                # (neigh + self)/2, :49-52
         training = self.training or not self.bn.track_running_stats
         if self.training and self.bn.track_running_stats:
             self.bn.num_batches_tracked += 1
