@@ -127,6 +127,12 @@ int jmac_bn_tanh_bwd_apply(const float* gout, const float* out, const float* pre
  * ------------------------------------------------------------------------------------------ */
 int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
                      float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+/* Weight-gradient product D[KO,N] = X[M,KO]^T . G[M,N] (reduction over the M node rows), same
+ * 3xTF32 scheme with both operands split in shared memory; KO in {128,256}, N % 32 == 0, N <= 256.
+ * Deterministic: per-CTA partials in `workspace` (jmac_gemm_tn_workspace_bytes) summed in order. */
+size_t jmac_gemm_tn_workspace_bytes(int KO, int N);
+int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, int64_t ldg, float* D, int64_t M,
+                        int KO, int N, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Completion scorer: TransE-L1 margin loss of JMAC.completion_loss (src/jmac_model.py:345-374)

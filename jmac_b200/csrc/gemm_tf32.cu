@@ -263,10 +263,219 @@ int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int K, int64_t
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight-gradient product  D[KO, N] = X[M, KO]^T . G[M, N]  (reduction over the M node rows).
+// Both operands are streamed row-major slabs, i.e. MN-major for the tensor core: a TMA box of
+// 32 features x 16 rows lands as sixteen 128-byte swizzled rows; a feature block of 128 (A) / N (B)
+// is a run of such boxes LBO = 2 KB apart, an 8-row K group is SBO = 1 KB inside a box.
+// Every CTA reduces a contiguous range of rows into two 128 x N accumulators in TMEM and writes its
+// partial [KO, N] to global memory; a second kernel sums the partials in a fixed order
+// (deterministic).  Both operands are split hi/lo in shared memory (3xTF32).
+// ------------------------------------------------------------------------------------------------
+constexpr int T_BR = 16;                                   // node rows per stage
+constexpr int T_BOX = 32 * T_BR * 4;                       // 2 KB: 32 features x 16 rows
+constexpr int T_OP = 8 * T_BOX;                            // 16 KB: 256 features x 16 rows
+constexpr int T_STAGE = 4 * T_OP;                          // X_hi, X_lo, G_hi, G_lo
+constexpr int T_SMEM = G_NS * T_STAGE + 1024 + 256;
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    // MN-major 32-bit operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte
+    // atoms (UMMA layout type 1, Swizzle<2,5,2>; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Its K atom is
+    // 4 rows of 128 B, so one K=8 MMA spans two atoms SBO = 512 B apart.
+    d |= (uint64_t)(T_BOX >> 4) << 16;      // leading byte offset: next 32-feature chunk
+    d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset: next 4-row K atom
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+struct GemmTnParams {
+    int M, KO, N;            // KO in {128, 256}, N % 32 == 0
+    int rows_per_cta;        // multiple of T_BR
+    float* partial;          // [gridDim.x, KO, N]
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tf32x3_tn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, GemmTnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + G_NS * T_STAGE;
+    const uint32_t tma_full0 = bars, xf_full0 = bars + 8 * G_NS, empty0 = bars + 16 * G_NS, acc_full = bars + 24 * G_NS, tmem_slot = acc_full + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * p.rows_per_cta;
+    const int row1 = min(p.M, row0 + p.rows_per_cta);
+    const int nst = row1 > row0 ? (row1 - row0 + T_BR - 1) / T_BR : 0;
+    const int xch = p.KO / 32, gch = p.N / 32;                 // 32-feature boxes per operand
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_NS; ++s) { mbar_init(tma_full0 + 8 * s, 1); mbar_init(xf_full0 + 8 * s, 8); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nst; ++it) {
+                const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
+                const uint32_t st = base + s * T_STAGE;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(tma_full0 + 8 * s, (uint32_t)(xch + gch) * T_BOX);
+                const int r = row0 + it * T_BR;
+                for (int c = 0; c < xch; ++c) tma_load_2d(st + c * T_BOX, &map_x, tma_full0 + 8 * s, c * 32, r);
+                for (int c = 0; c < gch; ++c) tma_load_2d(st + 2 * T_OP + c * T_BOX, &map_g, tma_full0 + 8 * s, c * 32, r);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nst > 0) {
+            // kind::tf32, A and B both MN-major (bits 15, 16), M = 128, N = p.N
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const int halves = p.KO / 128;
+            for (int it = 0; it < nst; ++it) {
+                const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
+                const uint32_t st = base + s * T_STAGE;
+                mbar_wait(xf_full0 + 8 * s, ph);
+                tc_fence_after();
+                for (int half = 0; half < halves; ++half) {
+                    const uint32_t d_tmem = tmem_base + half * 256;
+#pragma unroll
+                    for (int g = 0; g < T_BR / 8; ++g) {
+                        const uint64_t xhi = umma_desc_mn_sw128(st + half * 4 * T_BOX + g * 1024);
+                        const uint64_t xlo = umma_desc_mn_sw128(st + T_OP + half * 4 * T_BOX + g * 1024);
+                        const uint64_t ghi = umma_desc_mn_sw128(st + 2 * T_OP + g * 1024);
+                        const uint64_t glo = umma_desc_mn_sw128(st + 3 * T_OP + g * 1024);
+                        tc_mma_tf32(d_tmem, xhi, ghi, idesc, (it | g) != 0 ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, xlo, ghi, idesc, 1u);
+                        tc_mma_tf32(d_tmem, xhi, glo, idesc, 1u);
+                    }
+                }
+                tc_commit(empty0 + 8 * s);
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        const int w = warp - 2;
+        const int quarter = warp & 3, half = w >> 2;
+        for (int it = 0; it < nst; ++it) {
+            const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
+            mbar_wait(tma_full0 + 8 * s, ph);
+            // split X (first xch boxes of buffer 0 -> 0/1) and G (first gch boxes of buffer 2 -> 2/3)
+#pragma unroll
+            for (int op = 0; op < 2; ++op) {
+                float4* hi = reinterpret_cast<float4*>(gbase + s * T_STAGE + op * 2 * T_OP);
+                float4* lo = reinterpret_cast<float4*>(gbase + s * T_STAGE + op * 2 * T_OP + T_OP);
+                const int n4 = (op == 0 ? xch : gch) * (T_BOX / 16);
+                for (int i = w * 32 + lane; i < n4; i += 256) {
+                    const float4 x = hi[i];
+                    float4 h, l;
+                    h.x = tf32_rna(x.x); l.x = x.x - h.x;
+                    h.y = tf32_rna(x.y); l.y = x.y - h.y;
+                    h.z = tf32_rna(x.z); l.z = x.z - h.z;
+                    h.w = tf32_rna(x.w); l.w = x.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xf_full0 + 8 * s);
+        }
+        // ---- partial [KO, N] of this CTA -> global
+        float* prow = p.partial + ((size_t)blockIdx.x * p.KO + half * 128 + quarter * 32 + lane) * p.N;
+        const bool active = half * 128 < p.KO;
+        if (nst > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 256;
+            uint32_t raw[32];
+            for (int c = 0; c < p.N / 32; ++c) {
+                tc_ld32_issue(taddr + c * 32, raw);
+                tc_ld_wait();
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(prow + c * 32)[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                                                  __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                }
+            }
+        } else if (active) {
+            for (int c = 0; c < p.N / 4; ++c) reinterpret_cast<float4*>(prow)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+__global__ void sum_partials_f32_kernel(const float* __restrict__ partial, int n_part, int64_t n4, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < n_part; ++k) {
+        const float4 v = reinterpret_cast<const float4*>(partial)[(size_t)k * n4 + i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+}
+
+int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int feat, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return JMAC_EINVAL; }
+    cuuint64_t dims[2] = {(cuuint64_t)feat, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)T_BR};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f32, MN) failed with CUresult %d", (int)r); return JMAC_EINVAL; }
+    return 0;
+}
+
 }  // namespace
 }  // namespace jmac
 
 using namespace jmac;
+
+extern "C" size_t jmac_gemm_tn_workspace_bytes(int KO, int N) { return (size_t)sm_count() * (size_t)KO * (size_t)N * sizeof(float); }
+
+extern "C" int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, int64_t ldg, float* D, int64_t M, int KO, int N,
+                                   float* workspace, void* stream) {
+    JMAC_ARG(X && G && D && workspace && M > 0 && M < (int64_t(1) << 31));
+    JMAC_ARG((KO == 128 || KO == 256) && N >= 32 && N <= 256 && (N % 32) == 0);
+    JMAC_ARG(ldx >= KO && ldg >= N && (ldx % 4) == 0 && (ldg % 4) == 0);
+    JMAC_ARG(((uintptr_t)X % 16) == 0 && ((uintptr_t)G % 16) == 0 && ((uintptr_t)D % 16) == 0 && ((uintptr_t)workspace % 16) == 0);
+    CUtensorMap map_x, map_g;
+    int rc = make_map_f32_mn(&map_x, X, M, KO, ldx);
+    if (rc) return rc;
+    rc = make_map_f32_mn(&map_g, G, M, N, ldg);
+    if (rc) return rc;
+    const int64_t blocks_of_rows = (M + T_BR - 1) / T_BR;
+    int grid = sm_count();
+    if (blocks_of_rows < grid) grid = (int)blocks_of_rows;
+    GemmTnParams p;
+    p.M = (int)M; p.KO = KO; p.N = N;
+    p.rows_per_cta = (int)(((blocks_of_rows + grid - 1) / grid) * T_BR);
+    p.partial = workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    JMAC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    gemm_tf32x3_tn_kernel<<<grid, G_THREADS, T_SMEM, st>>>(map_x, map_g, p);
+    JMAC_LAUNCH_CHECK();
+    const int64_t n4 = (int64_t)KO * N / 4;
+    sum_partials_f32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(workspace, grid, n4, D);
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C, int64_t ldc,
                                 int64_t M, int N, int K, void* stream) {

@@ -197,6 +197,25 @@ def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor) -> torch.Tensor:
     return C
 
 
+def gemm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
+    """D[KO,N] = X[M,KO]^T @ G[M,N] (weight gradients: reduction over the node rows) through
+    jmac_gemm_tn_tf32x3."""
+    lib = _lib.load()
+    _need_cuda(X, G)
+    X, G = _f32c(X), _f32c(G)
+    M, KO = X.shape
+    N = G.shape[1]
+    D = torch.empty(KO, N, dtype=torch.float32, device=X.device)
+    ws = torch.empty(int(lib.jmac_gemm_tn_workspace_bytes(KO, N)) // 4, dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(lib.jmac_gemm_tn_tf32x3(ptr(X), KO, ptr(G), N, ptr(D), M, KO, N, ptr(ws), stream_ptr()), "jmac_gemm_tn_tf32x3")
+    return D
+
+
+def _tn_eligible(M, KO, N) -> bool:
+    return M >= 4096 and KO in (128, 256) and N % 32 == 0 and 32 <= N <= 256
+
+
 def _tc_eligible(M, K, N) -> bool:
     return M >= 4096 and N % 32 == 0 and 32 <= N <= 256 and K % 16 == 0 and K >= 16
 
@@ -218,7 +237,7 @@ class NodeMatmulFn(torch.autograd.Function):
             M, N = G.shape
             dX = gemm_nt(G, W.contiguous()) if _tc_eligible(M, N, W.shape[0]) else G @ W.t()
         if ctx.needs_input_grad[1]:
-            dW = X.t() @ G          # K x N reduction over all nodes: library GEMM for now
+            dW = gemm_tn(X, G) if _tn_eligible(X.shape[0], X.shape[1], G.shape[1]) else X.t() @ G
         return dX, dW
 
 

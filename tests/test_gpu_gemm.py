@@ -25,6 +25,20 @@ def test_gemm_tf32x3_matches_fp64(M, K, N):
     assert relerr(C, ref) < 5e-6
 
 
+@pytest.mark.parametrize("M,KO,N", [(5000, 256, 256), (4099, 128, 96), (70001, 256, 32), (16, 256, 256), (40000, 128, 256)])
+def test_gemm_tn_tf32x3_matches_fp64(M, KO, N):
+    """Weight-gradient product X^T G (MN-major operands, split-M partials, deterministic)."""
+    from jmac_b200 import functional as JF
+    torch.manual_seed(M + KO)
+    X = torch.randn(M, KO, device="cuda") * torch.exp(0.5 * torch.randn(M, 1, device="cuda"))
+    G = torch.randn(M, N, device="cuda")
+    D = JF.gemm_tn(X, G)
+    ref = X.double().t() @ G.double()
+    scale = X.double().abs().t() @ G.double().abs()
+    assert float(((D.double() - ref).abs() / scale).max()) < 2e-6
+    assert torch.equal(D, JF.gemm_tn(X, G))                      # fixed-order partial sums: bit-stable
+
+
 def test_node_mm_autograd_matches_torch():
     from jmac_b200 import functional as JF
     torch.manual_seed(0)

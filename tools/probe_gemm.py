@@ -8,8 +8,8 @@ def t(fn, n=5):
     for _ in range(n): fn()
     e.record(); torch.cuda.synchronize(); return s.elapsed_time(e) / n
 M, K, N = 2_000_000, 256, 256
-A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda") * 0.1
-print("tf32x3 kernel  %.3f ms" % t(lambda: JF.gemm_nt(A, B)))
-print("torch fp32 mm  %.3f ms" % t(lambda: A @ B.t()))
-torch.backends.cuda.matmul.allow_tf32 = True
-print("torch tf32 mm  %.3f ms" % t(lambda: A @ B.t()))
+A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda") * 0.1; G = torch.randn(M, N, device="cuda")
+print("NT tf32x3 kernel  %.3f ms" % t(lambda: JF.gemm_nt(A, B)))
+print("NT torch fp32 mm  %.3f ms" % t(lambda: A @ B.t()))
+print("TN tf32x3 kernel  %.3f ms" % t(lambda: JF.gemm_tn(A, G)))
+print("TN torch fp32 mm  %.3f ms" % t(lambda: A.t() @ G))
