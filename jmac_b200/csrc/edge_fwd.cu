@@ -141,6 +141,149 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Same computation with the row gathers moved off the register file: every warp owns a ring of
+// RING_S shared-memory slots; lane 0 issues one cp.async.bulk (TMA bulk copy, 1 instruction per row)
+// for each of Q[j], X[j], S[t], R'[t] of an edge into a slot and the whole warp waits on the slot's
+// mbarrier RING_S-1 edges later.  Memory latency is hidden by bytes in flight in shared memory
+// (12 warps x 7 slots x 2 KB per SM) instead of by occupancy; the LSU only sees conflict-free LDS.128.
+// The relation rows S[t], R'[t] are L2-resident: plain loads, prefetched one edge ahead in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int RING_WARPS = 12, RING_S = 8, RING_ROWS = 2;   // slot = {Q[j], X[j]}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+template <int VPL>
+__device__ __forceinline__ void lds_row(Row<VPL>& r, const float* base, int d4, int lane) {
+    const float4* p = reinterpret_cast<const float4*>(base);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = i * 32 + lane;
+        r.v[i] = c < d4 ? p[c] : f4_zero();
+    }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeFwdParams p) {
+    extern __shared__ __align__(16) uint8_t ring_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * RING_WARPS + wib;
+    const int nwarps = gridDim.x * RING_WARPS;
+    const int d4 = p.d4;
+    const uint32_t row_bytes = (uint32_t)d4 * 16;
+    const int row_f = d4 * 4;                                   // floats per row
+    float* slots = reinterpret_cast<float*>(ring_raw) + (size_t)wib * RING_S * RING_ROWS * row_f;
+    const uint32_t slots_s = smem_addr(slots);
+    const uint32_t bars = smem_addr(ring_raw) + (uint32_t)RING_WARPS * RING_S * RING_ROWS * row_bytes + (uint32_t)wib * RING_S * 8;
+    if (lane == 0) {
+        for (int s = 0; s < RING_S; ++s) mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    Row<VPL> av;
+    load_row<VPL, false>(av, p.a, 0, d4, lane);
+    uint32_t cnt_issue = 0, cnt_use = 0;                          // edges issued / consumed by this warp so far
+
+    for (int it = warp; it < p.n_items; it += nwarps) {
+        const Item item = p.items[it];
+        const int n = item.end - item.beg;
+        Row<VPL> pi;
+        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+        float m = -INFINITY, l = 0.f;
+        Row<VPL> acc;
+        acc.zero();
+        // indices are fetched 32 at a time but consumed 32 - RING_S at a time, so that the edge being
+        // issued (RING_S - 1 ahead of the one being consumed) is always inside the current batch
+        constexpr int ADV = 32 - RING_S;
+        int issued = 0;
+        Row<VPL> sn, rn;                                           // relation rows of the NEXT edge (L2-resident: register prefetch)
+        for (int base = 0; base < n; base += ADV) {
+            int jv = 0, tv = 0;
+            if (base + lane < n) {
+                jv = __ldg(p.csr_src + item.beg + base + lane);
+                tv = __ldg(p.csr_type + item.beg + base + lane);
+            }
+            if (base == 0) {
+                const int t0 = __shfl_sync(FULL, tv, 0);
+                load_row<VPL, false>(sn, p.S, t0, d4, lane);
+                load_row<VPL, false>(rn, p.Rp, t0, d4, lane);
+            }
+            const int lim = min(n, base + ADV);
+            for (int k = base; k < lim; ++k) {
+                // keep the ring full: issue the Q[j], X[j] gathers up to edge k + RING_S - 1
+                const int want = min(n, k + RING_S);
+                while (issued < want) {                           // warp-uniform
+                    const int j = __shfl_sync(FULL, jv, issued - base);
+                    if (lane == 0) {
+                        const uint32_t s = cnt_issue % RING_S;
+                        const uint32_t bar = bars + 8 * s, dst = slots_s + s * RING_ROWS * row_bytes;
+                        mbar_expect_tx(bar, RING_ROWS * row_bytes);
+                        bulk_row(dst, p.Q + (size_t)j * row_f, row_bytes, bar);
+                        bulk_row(dst + row_bytes, p.X + (size_t)j * row_f, row_bytes, bar);
+                    }
+                    ++cnt_issue;
+                    ++issued;
+                }
+                const Row<VPL> sr = sn, r = rn;
+                if (k + 1 < n) {                                  // prefetch the next edge's relation rows (k+1-base <= ADV < 32)
+                    const int t1 = __shfl_sync(FULL, tv, k + 1 - base);
+                    load_row<VPL, false>(sn, p.S, t1, d4, lane);
+                    load_row<VPL, false>(rn, p.Rp, t1, d4, lane);
+                }
+                const uint32_t s = cnt_use % RING_S;
+                mbar_wait(bars + 8 * s, (cnt_use / RING_S) & 1);
+                ++cnt_use;
+                const float* sl = slots + (size_t)s * RING_ROWS * row_f;
+                Row<VPL> q, x;
+                lds_row<VPL>(q, sl, d4, lane);
+                lds_row<VPL>(x, sl + row_f, d4, lane);
+                __syncwarp();                                     // every lane has its copy: the slot may be refilled
+                const float sc = warp_sum(leaky_dot<VPL>(pi, q, sr, av, p.slope));
+                const float mn = fmaxf(m, sc);
+                const float corr = __expf(m - mn);
+                const float pe = __expf(sc - mn);
+                l = l * corr + pe;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    acc.v[i] = corr * acc.v[i];
+                    fma4(acc.v[i], pe, x.v[i] - r.v[i]);
+                }
+                m = mn;
+            }
+        }
+        if (item.slot < 0) {
+            const float c = p.sqrt_deg[item.seg];
+            const float inv = l > 0.f ? c / l : 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
+            store_row<VPL>(acc, p.agg, item.seg, d4, lane);
+            if (lane == 0) p.lse[item.seg] = l > 0.f ? m + logf(l) : 0.f;
+        } else {
+            float* ps = p.partial + (size_t)item.slot * (size_t)(d4 * 4 + 4);
+            if (lane == 0) *reinterpret_cast<float4*>(ps) = make_float4(m, l, 0.f, 0.f);
+            store_row<VPL>(acc, ps + 4, 0, d4, lane);
+        }
+    }
+}
+
 // Two-level softmax merge for split (hub) destinations: one warp per split segment.
 template <int VPL>
 __global__ void __launch_bounds__(256) edge_fwd_merge_kernel(const Split* __restrict__ splits, int n_splits,
@@ -200,11 +343,25 @@ extern "C" int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, co
     }
     if (p.n_items == 0) return 0;
     const int threads = 256;
+    // The bulk-copy ring variant measures the same as the register-staged kernel on C4 (17.6-18.9 ms vs
+    // 18.4 ms: the bound is the memory system's random-1KB-gather rate, not latency hiding -- DESIGN.md
+    // section 4), so the simpler kernel stays the default; JMAC_EDGE_RING=1 selects the ring.
+    static const int use_ring = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 0;
+    const size_t ring_smem = (size_t)RING_WARPS * RING_S * (RING_ROWS * (size_t)d * 4 + 8);
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL == 1 ? 4 : 2;
-        auto kern = edge_fwd_kernel<VPL, U>;
-        int blocks = persistent_blocks(kern, threads, p.n_items);
-        kern<<<blocks, threads, 0, st>>>(p);
+        if (use_ring && ring_smem <= 220 * 1024) {
+            // bulk-copy ring variant: one CTA of 12 warps per SM
+            auto kern = edge_fwd_ring_kernel<VPL>;
+            JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+            long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
+            int blocks = (int)(want < sm_count() ? want : sm_count());
+            kern<<<blocks, RING_WARPS * 32, ring_smem, st>>>(p);
+        } else {
+            auto kern = edge_fwd_kernel<VPL, U>;
+            int blocks = persistent_blocks(kern, threads, p.n_items);
+            kern<<<blocks, threads, 0, st>>>(p);
+        }
         JMAC_LAUNCH_CHECK();
         if (plan->dst_items.n_splits > 0) {
             int mb = (plan->dst_items.n_splits * 32 + threads - 1) / threads;
