@@ -74,6 +74,13 @@ int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, const float* 
                   const float* Rp, const float* a_att, float leaky_slope, int d, float* agg,
                   float* lse, void* stream);
 
+/* Same, with the self-loop propagate of src/jmac_model.py:50 fused into the epilogue: additionally
+ * writes T[i] = agg[i] + Xself[i] - Rp[n_rel-1] (the operand of the message GEMM), Xself being the
+ * [N_dst,d] table of the destinations' own embeddings.  Xself and T are both NULL or both set. */
+int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float* Q, const float* X,
+                        const float* S, const float* Rp, const float* a_att, float leaky_slope, int d,
+                        float* agg, float* lse, const float* Xself, float* T, void* stream);
+
 /* Bytes per edge of the opaque record buffer `erec` that backward passes share. */
 size_t jmac_edge_record_bytes(int d);
 

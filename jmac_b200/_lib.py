@@ -24,6 +24,7 @@ _SIGNATURES = {
     "jmac_plan_info": (c_int, [P, POINTER(c_int64)]),
     "jmac_plan_export": (c_int, [P, P, P, P, P, P, P]),
     "jmac_edge_fwd": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P]),
+    "jmac_edge_fwd_fused": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "jmac_edge_record_bytes": (c_size_t, [c_int]),
     "jmac_edge_bwd_dst": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P, P]),
     "jmac_edge_bwd_src": (c_int, [P, P, P, P, c_float, c_int, P, P, P]),

@@ -29,7 +29,22 @@ struct EdgeFwdParams {
     float* agg;
     float* lse;
     float* partial;  // [n_slots, d + 4]: (m, l, -, -) then the un-normalised weighted sum
+    // optional fused self-loop term: T[i] = agg[i] + Xself[i] - loop_row  (all three null or all set)
+    const float* Xself;
+    const float* loop_row;
+    float* T;
 };
+
+// T = agg + X[i] - R'[loop]: the operand of the message GEMM ((neigh + self) W_g, src/jmac_model.py:49-52)
+template <int VPL>
+__device__ __forceinline__ void store_self_fused(const EdgeFwdParams& p, const Row<VPL>& agg_row, int seg, int d4, int lane) {
+    Row<VPL> xs, lr;
+    load_row<VPL, true>(xs, p.Xself, seg, d4, lane);
+    load_row<VPL, false>(lr, p.loop_row, 0, d4, lane);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) xs.v[i] = agg_row.v[i] + xs.v[i] - lr.v[i];
+    store_row<VPL>(xs, p.T, seg, d4, lane);
+}
 
 template <int VPL>
 __device__ __forceinline__ float leaky_dot(const Row<VPL>& pi, const Row<VPL>& q, const Row<VPL>& s, const Row<VPL>& a, float slope) {
@@ -132,6 +147,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
 #pragma unroll
             for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
             store_row<VPL>(acc, p.agg, item.seg, d4, lane);
+            if (p.T) store_self_fused<VPL>(p, acc, item.seg, d4, lane);
             if (lane == 0) p.lse[item.seg] = l > 0.f ? m + logf(l) : 0.f;
         } else {
             float* ps = p.partial + (size_t)item.slot * (size_t)(d4 * 4 + 4);
@@ -275,6 +291,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
 #pragma unroll
             for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
             store_row<VPL>(acc, p.agg, item.seg, d4, lane);
+            if (p.T) store_self_fused<VPL>(p, acc, item.seg, d4, lane);
             if (lane == 0) p.lse[item.seg] = l > 0.f ? m + logf(l) : 0.f;
         } else {
             float* ps = p.partial + (size_t)item.slot * (size_t)(d4 * 4 + 4);
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
 
 // Two-level softmax merge for split (hub) destinations: one warp per split segment.
 template <int VPL>
-__global__ void __launch_bounds__(256) edge_fwd_merge_kernel(const Split* __restrict__ splits, int n_splits,
+__global__ void __launch_bounds__(256) edge_fwd_merge_kernel(EdgeFwdParams fp, const Split* __restrict__ splits, int n_splits,
                                                              const float* __restrict__ partial, const float* __restrict__ sqrt_deg,
                                                              int d4, float* __restrict__ agg, float* __restrict__ lse) {
     const int lane = threadIdx.x & 31;
@@ -314,6 +331,7 @@ __global__ void __launch_bounds__(256) edge_fwd_merge_kernel(const Split* __rest
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
     store_row<VPL>(acc, agg, sp.seg, d4, lane);
+    if (fp.T) store_self_fused<VPL>(fp, acc, sp.seg, d4, lane);
     if (lane == 0) lse[sp.seg] = L > 0.f ? M + logf(L) : 0.f;
 }
 
@@ -323,7 +341,14 @@ using namespace jmac;
 
 extern "C" int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S, const float* Rp,
                              const float* a_att, float leaky_slope, int d, float* agg, float* lse, void* stream) {
+    return jmac_edge_fwd_fused(plan, P, Q, X, S, Rp, a_att, leaky_slope, d, agg, lse, nullptr, nullptr, stream);
+}
+
+extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S, const float* Rp,
+                                   const float* a_att, float leaky_slope, int d, float* agg, float* lse, const float* Xself, float* T,
+                                   void* stream) {
     JMAC_ARG(plan && P && Q && X && S && Rp && a_att && agg && lse);
+    JMAC_ARG((Xself == nullptr) == (T == nullptr));
     JMAC_ARG(dim_ok(d));
     cudaStream_t st = (cudaStream_t)stream;
     EdgeFwdParams p;
@@ -336,6 +361,8 @@ extern "C" int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, co
     p.slope = leaky_slope;
     p.d4 = d / 4;
     p.agg = agg; p.lse = lse;
+    p.Xself = Xself; p.T = T;
+    p.loop_row = Rp + (size_t)(plan->n_rel - 1) * d;     // the self-loop relation is the last row of R'
     p.partial = nullptr;
     if (plan->dst_items.n_slots > 0) {
         int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)(d + 4), &p.partial);
@@ -365,7 +392,7 @@ extern "C" int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, co
         JMAC_LAUNCH_CHECK();
         if (plan->dst_items.n_splits > 0) {
             int mb = (plan->dst_items.n_splits * 32 + threads - 1) / threads;
-            edge_fwd_merge_kernel<VPL><<<mb, threads, 0, st>>>(plan->dst_items.splits, plan->dst_items.n_splits, p.partial,
+            edge_fwd_merge_kernel<VPL><<<mb, threads, 0, st>>>(p, plan->dst_items.splits, plan->dst_items.n_splits, p.partial,
                                                                 plan->sqrt_deg, p.d4, agg, lse);
             JMAC_LAUNCH_CHECK();
         }

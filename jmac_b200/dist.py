@@ -187,8 +187,8 @@ def sharded_layer_forward(layer, x_loc, rel_emb, shard: Shard, plan, group, ops=
     S = torch.mm(Rp, layer.w_att[d:])
     wait_gather(Xf)
     Qf = mm(Xf, layer.w_att[d:])
-    agg = ops.edge_phase(plan, P, Qf, Xf, S, Rp, layer.a_att, layer.leaky_slope)
-    pre = mm(agg + x_loc - Rp[-1], layer.gcn_weight * 0.5)
+    T = ops.edge_phase(plan, P, Qf, Xf, S, Rp, layer.a_att, layer.leaky_slope, x_loc)     # self-loop term fused
+    pre = mm(T, layer.gcn_weight * 0.5)
     training = layer.training or not layer.bn.track_running_stats
     if layer.training and layer.bn.track_running_stats:
         layer.bn.num_batches_tracked += 1

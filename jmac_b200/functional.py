@@ -124,10 +124,12 @@ def clear_plan_cache():
 # edge phase
 # ----------------------------------------------------------------------------------------------
 class EdgePhaseFn(torch.autograd.Function):
-    """agg[i] = sqrt(deg_i) * sum_e softmax_i(a . lrelu(P[i]+Q[j]-S[t])) * (X[j] - Rp[t])."""
+    """agg[i] = sqrt(deg_i) * sum_e softmax_i(a . lrelu(P[i]+Q[j]-S[t])) * (X[j] - Rp[t]).
+    With ``Xself`` ([N_dst,d], the destinations' own rows) the self-loop propagate is fused and the
+    result is T = agg + Xself - Rp[-1] (src/jmac_model.py:49-52 before the message GEMM)."""
 
     @staticmethod
-    def forward(ctx, plan: GraphPlan, P, Q, X, S, Rp, a_att, slope: float):
+    def forward(ctx, plan: GraphPlan, P, Q, X, S, Rp, a_att, slope: float, Xself=None):
         _need_cuda(P, Q, X, S, Rp, a_att)
         lib = _lib.load()
         P, Q, X, S, Rp, a = (_f32c(t) for t in (P, Q, X, S, Rp, a_att.reshape(-1)))
@@ -136,13 +138,19 @@ class EdgePhaseFn(torch.autograd.Function):
             raise ValueError("table sizes do not match the graph plan")
         agg = torch.empty_like(P)
         lse = torch.empty(N, dtype=torch.float32, device=X.device)
+        T = None
+        if Xself is not None:
+            Xself = _f32c(Xself)
+            if Xself.shape != P.shape:
+                raise ValueError("Xself must be [N_dst, d]")
+            T = torch.empty_like(P)
         with torch.cuda.device(X.device):
-            check(lib.jmac_edge_fwd(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
-                                    stream_ptr()), "jmac_edge_fwd")
-        ctx.plan, ctx.slope = plan, float(slope)
+            check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
+                                          ptr(Xself), ptr(T), stream_ptr()), "jmac_edge_fwd")
+        ctx.plan, ctx.slope, ctx.fused = plan, float(slope), Xself is not None
         ctx.save_for_backward(P, Q, X, S, Rp, a, agg, lse)
         ctx.a_shape = a_att.shape
-        return agg
+        return T if T is not None else agg
 
     @staticmethod
     def backward(ctx, g):
@@ -166,11 +174,15 @@ class EdgePhaseFn(torch.autograd.Function):
                                         ptr(dP), ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
             check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(dXe), ptr(dQ), st), "jmac_edge_bwd_src")
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(dRp), ptr(dS), st), "jmac_edge_bwd_rel")
-        return None, dP, dQ, dXe, dS, dRp, da.view(ctx.a_shape), None
+        dXself = None
+        if ctx.fused:
+            dXself = G                                  # T = agg + Xself - Rp[-1]
+            dRp[-1] -= G.sum(0)
+        return None, dP, dQ, dXe, dS, dRp, da.view(ctx.a_shape), None, dXself
 
 
-def edge_phase(plan, P, Q, X, S, Rp, a_att, slope):
-    return EdgePhaseFn.apply(plan, P, Q, X, S, Rp, a_att, slope)
+def edge_phase(plan, P, Q, X, S, Rp, a_att, slope, Xself=None):
+    return EdgePhaseFn.apply(plan, P, Q, X, S, Rp, a_att, slope, Xself)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -81,8 +81,8 @@ class RelationAwareLayer(nn.Module):
         P = JF.node_mm(X, self.w_att[:d])           # node tables: 3xTF32 tcgen05 GEMM (fp32-accurate), small ones: library
         Q = JF.node_mm(X, self.w_att[d:])
         S = torch.mm(Rp, self.w_att[d:])
-        agg = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope)   # neighbours, pre-GEMM
-        pre = JF.node_mm(agg + X - Rp[-1], self.gcn_weight * 0.5)                # (neigh + self)/2, :49-52
+        T = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope, X)  # agg + X - R'[loop] (self-loop fused)
+        pre = JF.node_mm(T, self.gcn_weight * 0.5)                               # (neigh + self)/2, :49-52
         training = self.training or not self.bn.track_running_stats
         if self.training and self.bn.track_running_stats:
             self.bn.num_batches_tracked += 1

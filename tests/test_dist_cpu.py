@@ -45,13 +45,14 @@ class CpuOps:
             self.N_src = n_src if n_src is not None else num_ent
 
     @staticmethod
-    def edge_phase(plan, P, Q, X, S, Rp, a_att, slope):
+    def edge_phase(plan, P, Q, X, S, Rp, a_att, slope, Xself=None):
         row, col, t = plan.ei[0], plan.ei[1], plan.et
         z = P[row] + Q[col] - S[t]
         s = O.leaky_relu(z, slope) @ a_att.reshape(-1, 1)
         alpha = O.scatter_softmax(s, row, plan.N)
         deg = torch.bincount(row, minlength=plan.N).to(P.dtype)
-        return O.scatter_sum(alpha * deg.sqrt()[row].view(-1, 1) * (X[col] - Rp[t]), row, plan.N)
+        agg = O.scatter_sum(alpha * deg.sqrt()[row].view(-1, 1) * (X[col] - Rp[t]), row, plan.N)
+        return agg if Xself is None else agg + Xself - Rp[-1]
 
     @staticmethod
     def bn_tanh(pre, gamma, beta, rm, rv, momentum, eps, training, group):
