@@ -244,28 +244,41 @@ def run_b200(args):
             P, Q, S = x0 @ layers[0].w_att[:d], x0 @ layers[0].w_att[d:], Rp @ layers[0].w_att[d:]
             a = layers[0].a_att.reshape(-1).contiguous()
             X = x0.detach()
-        agg, lse = torch.empty_like(X), torch.empty(N, device=dev)
+        agg, lse, Tbuf = torch.empty_like(X), torch.empty(N, device=dev), torch.empty_like(X)
         dP, dXe, dQ = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
         dRp, dS, da = torch.empty_like(Rp), torch.empty_like(Rp), torch.zeros(d, device=dev)
         rec = int(lib.jmac_edge_record_bytes(d))
         erec = torch.empty(E * rec, dtype=torch.uint8, device=dev)
         ptr, st = _lib.ptr, _lib.stream_ptr
-        k_fwd = lambda: _lib.check(lib.jmac_edge_fwd(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), 0.05, d, ptr(agg), ptr(lse), st()))
-        k_dst = lambda: _lib.check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), 0.05, d, ptr(agg), ptr(lse),
-                                                         ptr(gout), ptr(dP), ptr(erec), ptr(da), st()))
-        k_src = lambda: _lib.check(lib.jmac_edge_bwd_src(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(dXe), ptr(dQ), st()))
-        k_rel = lambda: _lib.check(lib.jmac_edge_bwd_rel(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(dRp), ptr(dS), st()))
+        # the kernels exactly as a training step launches them (self-loop fused, per-edge record saved)
+        k_fwd = lambda: _lib.check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), 0.05, d, ptr(agg),
+                                                           ptr(lse), ptr(X), ptr(Tbuf), ptr(erec), st()))
+        k_dst = lambda: _lib.check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(X), ptr(Rp), ptr(a), 0.05, d, ptr(agg), ptr(lse), ptr(gout),
+                                                         ptr(dP), ptr(erec), ptr(da), st()))
+        k_src = lambda: _lib.check(lib.jmac_edge_bwd_src(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st()))
+        k_rel = lambda: _lib.check(lib.jmac_edge_bwd_rel(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st()))
         row = d * 4
+        mrec = rec - 12                     # sign mask bytes; the record is {w, ds} 8 B + mask + logit 4 B
         algo = {  # algorithmic HBM bytes per launch
-            "edge_fwd": E * (2 * row + 8) + N * (2 * row + 28),
-            "edge_bwd_dst": E * (2 * row + 8 + rec) + N * (4 * row + 28),
-            "edge_bwd_src": E * (row + 8 + rec) + N * (2 * row + 20),
-            "edge_bwd_rel": E * (row + 8 + rec) + (R + 1) * 2 * row,
+            "edge_fwd": E * (2 * row + 8 + mrec + 4) + N * (5 * row + 28),          # P, Xself read; agg, T written (+ item)
+            "edge_bwd_dst": E * (row + 8 + mrec + 4 + 8) + N * (4 * row + 28),      # G, agg, P read; dP written
+            "edge_bwd_src": E * (row + 8 + 8 + mrec) + N * (3 * row + 20),          # Q read; dXe, dQ written
+            "edge_bwd_rel": E * (row + 8 + 8 + mrec) + (R + 1) * 3 * row,
         }
         kernels = {}
         for name, fn in (("edge_fwd", k_fwd), ("edge_bwd_dst", k_dst), ("edge_bwd_src", k_src), ("edge_bwd_rel", k_rel)):
             t = event_time(fn, 3, 10)
             kernels[name] = {"ms": t, "algo_bytes": algo[name], "GBps": algo[name] / t / 1e6, "frac": algo[name] / t / 1e6 / hbm_peak}
+        # context: what a trivial kernel gets on the same access pattern (random 1 KiB rows of a 2 GB table):
+        # jmac_pair_cos_fwd reads two random rows per pair and writes 4 bytes
+        npair = E // 2
+        ia = torch.randint(0, N, (npair,), device=dev)
+        ib = torch.randint(0, N, (npair,), device=dev)
+        cosv = torch.empty(npair, device=dev)
+        k_gather = lambda: _lib.check(lib.jmac_pair_cos_fwd(ptr(X), ptr(gout), d, ptr(ia), ptr(ib), npair, ptr(cosv), st()))
+        t_g = event_time(k_gather, 3, 10)
+        gather_gbps = npair * (2 * row + 20) / t_g / 1e6
+        del ia, ib, cosv
         top = max(kernels, key=lambda k: kernels[k]["ms"])
         edge_ms = sum(v["ms"] for v in kernels.values())
         edge_bytes = sum(v["algo_bytes"] for v in kernels.values())
@@ -273,8 +286,12 @@ def run_b200(args):
                             "frac": kernels[top]["frac"], "traffic": TRAFFIC_NCU.get(top), "peak_source": peak_src,
                             "edge_phase_fwd_bwd": {"ms": edge_ms, "GBps": edge_bytes / edge_ms / 1e6, "frac": edge_bytes / edge_ms / 1e6 / hbm_peak,
                                                    "edges_per_s": E / (edge_ms * 1e-3)},
+                            "random_row_gather_GBps": gather_gbps,
+                            "random_row_gather_note": "jmac_pair_cos_fwd on 20M random row pairs: the rate the memory system sustains for "
+                                                      "random 1 KiB-row gathers (ncu: DRAM busy but ~72% efficient, 256 B per channel per row); "
+                                                      "the edge kernels' frac stays quoted against the streaming copy peak",
                             "kernels": kernels}
-        del agg, lse, dP, dXe, dQ, erec, P, Q
+        del agg, lse, Tbuf, dP, dXe, dQ, erec, P, Q
 
     if single and "scorer" in sections:
         # ---- completion scorer, fwd+bwd, reference batch layout
@@ -366,7 +383,7 @@ def run_b200(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # of this same workload (profiles/ncu_edge_kernels_r01.md); bytes.
-TRAFFIC_NCU = {"edge_fwd": 86.03e9, "edge_bwd_dst": 91.86e9, "edge_bwd_src": 55.31e9, "edge_bwd_rel": 49.88e9}
+TRAFFIC_NCU = {}      # filled from profiles/ncu_edge_kernels_r01.md once the final kernels are captured
 
 
 def main():

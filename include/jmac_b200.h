@@ -74,33 +74,42 @@ int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, const float* 
                   const float* Rp, const float* a_att, float leaky_slope, int d, float* agg,
                   float* lse, void* stream);
 
-/* Same, with the self-loop propagate of src/jmac_model.py:50 fused into the epilogue: additionally
- * writes T[i] = agg[i] + Xself[i] - Rp[n_rel-1] (the operand of the message GEMM), Xself being the
- * [N_dst,d] table of the destinations' own embeddings.  Xself and T are both NULL or both set. */
+/* Same, with two optional fusions:
+ *  - Xself/T (both NULL or both set): the self-loop propagate of src/jmac_model.py:50 is folded into
+ *    the epilogue, T[i] = agg[i] + Xself[i] - Rp[n_rel-1] (the operand of the message GEMM), Xself
+ *    being the [N_dst,d] table of the destinations' own embeddings;
+ *  - erec (NULL when no gradient is needed): the per-edge record buffer of
+ *    E * jmac_edge_record_bytes(d) bytes; forward stores the attention logit s_e and the sign mask of
+ *    z_e = P[i]+Q[j]-S[t] (1 bit per feature) of every edge, which is all backward needs of P, Q, S. */
 int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float* Q, const float* X,
                         const float* S, const float* Rp, const float* a_att, float leaky_slope, int d,
-                        float* agg, float* lse, const float* Xself, float* T, void* stream);
+                        float* agg, float* lse, const float* Xself, float* T, void* erec,
+                        void* stream);
 
-/* Bytes per edge of the opaque record buffer `erec` that backward passes share. */
+/* Bytes per edge of the record buffer `erec` shared by forward and the backward passes
+ * ({alpha*sqrt(deg), ds_e} 8 B + sign mask 32/64 B + logit 4 B). */
 size_t jmac_edge_record_bytes(int d);
 
-/* Backward, destination pass (atomics-free over the CSR): given G = dL/d agg, recomputes the
- * logits, writes dP[N,d] (= dL/dP), the per-edge record (alpha*sqrt(deg), ds_e, sign mask of the
- * LeakyReLU argument) into erec[E*jmac_edge_record_bytes(d)] and ACCUMULATES da_att[d] (caller
- * zeroes it).  Autograd of src/jmac_model.py:75-76,88 and message_passing.py:24-28. */
-int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* Q, const float* X,
-                      const float* S, const float* Rp, const float* a_att, float leaky_slope, int d,
-                      const float* agg, const float* lse, const float* G, float* dP, void* erec,
-                      float* da_att, void* stream);
-/* Backward, source pass (atomics-free over the by-source ordering): dXe[N,d] = sum over out-edges
- * of alpha*sqrt(deg)*G[i]  (the x_j gather's gradient, replaces index_put_(accumulate)), and
- * dQ[N,d] = sum over out-edges of ds_e * a_att * LeakyReLU'(z_e). */
+/* Backward of src/jmac_model.py:56-89 + message_passing.py:24-28 in three atomics-free segmented
+ * passes, each gathering ONE node row per edge.  G = dL/d agg ([N_dst,d]).  Every pass ACCUMULATES its
+ * term of da_att[d] (caller zeroes it once): LeakyReLU is positively homogeneous, so
+ * d a = sum_i P[i](.)mu_i + sum_j Q[j](.)nu_j - sum_t S[t](.)omega_t with the per-segment sums of
+ * ds_e * LeakyReLU'(z_e) that the passes form anyway.
+ * Destination pass: reads the forward's logits and masks from erec, gathers X[j]; writes dP[N_dst,d]
+ * and the {alpha*sqrt(deg), ds_e} part of erec. */
+int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X, const float* Rp,
+                      const float* a_att, float leaky_slope, int d, const float* agg, const float* lse,
+                      const float* G, float* dP, void* erec, float* da_att, void* stream);
+/* Source pass (by-source ordering): dXe[N_src,d] = sum over out-edges of alpha*sqrt(deg)*G[i] (the
+ * x_j gather's gradient, replaces index_put_(accumulate)); dQ[N_src,d] = a_att (.) nu_j. */
 int jmac_edge_bwd_src(jmac_plan* plan, const float* G, const void* erec, const float* a_att,
-                      float leaky_slope, int d, float* dXe, float* dQ, void* stream);
-/* Backward, relation pass (by-relation ordering): dRp[n_rel,d] -= sum alpha*sqrt(deg)*G[i],
- * dS[n_rel,d] -= sum ds_e * a_att * LeakyReLU'(z_e).  Tables are overwritten (zeroed inside). */
+                      float leaky_slope, int d, const float* Q, float* dXe, float* dQ, float* da_att,
+                      void* stream);
+/* Relation pass (by-relation ordering): dRp[n_rel,d] = -sum alpha*sqrt(deg)*G[i],
+ * dS[n_rel,d] = -a_att (.) omega_t.  Tables are overwritten (zeroed inside). */
 int jmac_edge_bwd_rel(jmac_plan* plan, const float* G, const void* erec, const float* a_att,
-                      float leaky_slope, int d, float* dRp, float* dS, void* stream);
+                      float leaky_slope, int d, const float* S, float* dRp, float* dS, float* da_att,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm1d over the N nodes + tanh (src/jmac_model.py:52), split so that a multi-GPU caller can

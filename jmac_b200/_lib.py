@@ -24,11 +24,11 @@ _SIGNATURES = {
     "jmac_plan_info": (c_int, [P, POINTER(c_int64)]),
     "jmac_plan_export": (c_int, [P, P, P, P, P, P, P]),
     "jmac_edge_fwd": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P]),
-    "jmac_edge_fwd_fused": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
+    "jmac_edge_fwd_fused": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
     "jmac_edge_record_bytes": (c_size_t, [c_int]),
-    "jmac_edge_bwd_dst": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P, P]),
-    "jmac_edge_bwd_src": (c_int, [P, P, P, P, c_float, c_int, P, P, P]),
-    "jmac_edge_bwd_rel": (c_int, [P, P, P, P, c_float, c_int, P, P, P]),
+    "jmac_edge_bwd_dst": (c_int, [P, P, P, P, P, c_float, c_int, P, P, P, P, P, P, P]),
+    "jmac_edge_bwd_src": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
+    "jmac_edge_bwd_rel": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "jmac_bn_stats": (c_int, [P, c_int64, c_int, P, P]),
     "jmac_bn_tanh_apply": (c_int, [P, c_int64, c_int, P, c_int64, P, P, P, P, c_float, c_float, c_int, P, P, P, P]),
     "jmac_bn_tanh_bwd_stats": (c_int, [P, P, P, c_int64, c_int, P, P, P, P]),

@@ -144,6 +144,40 @@ __device__ __forceinline__ void store_row(const Row<VPL>& r, float* base, int64_
         if (c < d4) p[c] = r.v[i];
     }
 }
+// ---- per-warp shared-memory rings fed by cp.async.bulk (TMA bulk copies): latency is hidden by bytes in
+// flight in shared memory instead of registers/occupancy.  One CTA of RING_WARPS warps per SM.
+constexpr int RING_WARPS = 16;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+template <int VPL>
+__device__ __forceinline__ void lds_row(Row<VPL>& r, const float* base, int d4, int lane) {
+    const float4* p = reinterpret_cast<const float4*>(base);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = i * 32 + lane;
+        r.v[i] = c < d4 ? p[c] : f4_zero();
+    }
+}
+
+
 // grid for a persistent warp-per-item kernel: enough blocks to fill every SM at the kernel's
 // occupancy, never more than the work needs.
 template <typename K>
@@ -169,5 +203,19 @@ inline int persistent_blocks(K kernel, int threads, int n_warp_items) {
     } while (0)
 
 inline bool dim_ok(int d) { return d >= 4 && d <= 512 && (d % 4) == 0; }
+
+// Per-edge record shared by the forward (writes logit + mask) and backward passes, in CSR order:
+//   [0, 8E)            float2 {w_e = alpha_e sqrt(deg_i), ds_e}                 (backward dst pass)
+//   [8E, 8E + MB*E)    sign mask of z_e: lane l of the warp owns MB/32 bytes   (forward)
+//   then               float logit s_e                                          (forward)
+template <int VPL> struct MaskT { typedef uint8_t type; };
+template <> struct MaskT<3> { typedef uint16_t type; };
+template <> struct MaskT<4> { typedef uint16_t type; };
+inline size_t edge_mask_bytes(int d) { return (((d / 4 + 31) / 32) <= 2) ? 32 : 64; }
+inline float2* erec_ew(void* erec) { return reinterpret_cast<float2*>(erec); }
+inline void* erec_mask(void* erec, int64_t E) { return reinterpret_cast<char*>(erec) + sizeof(float2) * (size_t)E; }
+inline float* erec_logit(void* erec, int64_t E, int d) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(erec) + (sizeof(float2) + edge_mask_bytes(d)) * (size_t)E);
+}
 
 }  // namespace jmac

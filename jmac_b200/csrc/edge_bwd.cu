@@ -1,27 +1,26 @@
 // Backward of the edge phase (autograd of src/jmac_model.py:56-89 + message_passing.py:24-28, which
 // the reference gets from index_put_(accumulate) atomics and E-row GEMM transposes).
 //
-// Three atomics-free segmented passes over the three edge orderings of the plan:
-//   dst pass : per destination i  -> dP[i]; per-edge record {w_e = alpha_e*sqrt(deg_i), ds_e,
-//              sign mask of z_e = P[i]+Q[j]-S[t]}; da_att.  Gathers Q[j], X[j] (2 rows / edge).
-//   src pass : per source j       -> dXe[j] = sum w_e G[i],  dQ[j] = sum ds_e a (.) lrelu'(z_e).
-//              Gathers G[i] (1 row / edge) + the 8+MB byte record.
-//   rel pass : per relation t     -> dR'[t] = -sum w_e G[i], dS[t] = -sum ds_e a (.) lrelu'(z_e).
-//              Gathers G[i] (1 row / edge) + the record.
-// The sign mask (1 bit per feature, 32 B per edge at d=256) is what lets the src and rel passes
-// rebuild d z_e without re-gathering P[i], Q[j], S[t] (3 KB per edge).
-// Algorithmic HBM bytes per edge: dst 2*d*4 + 8 + rec, src d*4 + 8 + rec, rel d*4 + 8 + rec.
+// Forward saves, per CSR position, the attention logit s_e (4 B) and the sign mask of
+// z_e = P[i]+Q[j]-S[t] (1 bit per feature: 32 B at d=256).  With those, three atomics-free segmented
+// passes over the three edge orderings of the plan need ONE gathered node row per edge each:
+//   dst pass : per destination i -> alpha_e = exp(s_e - lse_i), u_e = G[i].(X[j]-R'[t]),
+//              ds_e = alpha_e (sqrt(deg_i) u_e - G[i].agg[i]);  mu_i = sum_e ds_e lrelu'(z_e);
+//              dP[i] = a (.) mu_i;  record {w_e = alpha_e sqrt(deg_i), ds_e}.       gathers X[j]
+//   src pass : per source j  -> dXe[j] = sum w_e G[i],  nu_j = sum ds_e lrelu'(z_e), dQ[j] = a (.) nu_j.
+//                                                                                    gathers G[i]
+//   rel pass : per relation t -> dR'[t] = -sum w_e G[i], dS[t] = -a (.) omega_t.      gathers G[i]
+// The sign mask is what lets every pass rebuild d z_e = ds_e a (.) lrelu'(z_e) without re-gathering
+// P[i], Q[j], S[t].  The gradient of a_att needs lrelu(z_e) itself; LeakyReLU is positively
+// homogeneous (lrelu(z) = z lrelu'(z)), so
+//     d a = sum_e ds_e lrelu(z_e) = sum_i P[i] (.) mu_i + sum_j Q[j] (.) nu_j - sum_t S[t] (.) omega_t,
+// three node-level terms that each pass accumulates at segment end (one extra row read per segment).
+// Algorithmic HBM bytes per edge (d=256): dst 1 KiB + 56, src 1 KiB + 48, rel 1 KiB + 48.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace jmac {
-
-template <int VPL> struct MaskT { typedef uint8_t type; };
-template <> struct MaskT<3> { typedef uint16_t type; };
-template <> struct MaskT<4> { typedef uint16_t type; };
-
-static inline size_t mask_bytes(int d) { return (((d / 4 + 31) / 32) <= 2) ? 32 : 64; }
 
 struct EdgeBwdDstParams {
     const Item* items;
@@ -29,16 +28,36 @@ struct EdgeBwdDstParams {
     const int* csr_src;
     const int* csr_type;
     const float* sqrt_deg;
-    const float *P, *Q, *X, *S, *Rp, *a;
+    const float *P, *X, *Rp, *a;
     float slope;
     int d4;
     const float *agg, *lse, *G;
     float* dP;
-    float2* ew;     // [E] (w_e, ds_e)
-    void* mask;     // [E][32] lanes x MaskT
-    float* da;      // [d] accumulated
-    float* partial; // [n_slots, d]
+    float2* ew;          // [E] (w_e, ds_e)                      out
+    const void* mask;    // [E][32] lanes x mask_t               in (forward)
+    const float* logit;  // [E]                                  in (forward)
+    float* da;           // [d] accumulated
+    float* partial;      // [n_slots, d]
 };
+
+// block-level reduction of the per-warp d a_att contributions, then one vector RED per feature per block
+template <int VPL, int NW>
+__device__ __forceinline__ void flush_da_nw(const Row<VPL>& da_acc, float* da, int d4) {
+    __shared__ float4 red[NW][VPL * 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) red[wib][i * 32 + lane] = da_acc.v[i];
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < d4; c4 += blockDim.x) {
+        float4 s = red[0][c4];
+        for (int w = 1; w < NW; ++w) s = s + red[w][c4];
+        red_add_v4(da + 4 * c4, s);
+    }
+}
+template <int VPL>
+__device__ __forceinline__ void flush_da(const Row<VPL>& da_acc, float* da, int d4) { flush_da_nw<VPL, 8>(da_acc, da, d4); }
+template <int VPL>
+__device__ __forceinline__ void flush_da16(const Row<VPL>& da_acc, float* da, int d4) { flush_da_nw<VPL, RING_WARPS>(da_acc, da, d4); }
 
 template <int VPL, int U>
 __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
@@ -50,15 +69,15 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
     Row<VPL> av, da_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     da_acc.zero();
-    mask_t* maskp = reinterpret_cast<mask_t*>(p.mask);
+    const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
+    const float hi = 1.f - p.slope;
 
     for (int it = warp; it < p.n_items; it += nwarps) {
         const Item item = p.items[it];
-        Row<VPL> pi, gi, dp_acc;
-        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+        Row<VPL> gi, mu;          // mu: sum over edges with z > 0 of ds_e, per feature
         load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
-        dp_acc.zero();
-        float gdot = 0.f;
+        mu.zero();
+        float gdot = 0.f, ds_sum = 0.f;
         {
             Row<VPL> ai;
             load_row<VPL, true>(ai, p.agg, item.seg, d4, lane);
@@ -71,87 +90,75 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
         for (int base = item.beg; base < item.end; base += 32) {
             const int cnt = min(32, item.end - base);
             int jv = 0, tv = 0;
+            float sv = 0.f;
             if (lane < cnt) {
                 jv = __ldg(p.csr_src + base + lane);
                 tv = __ldg(p.csr_type + base + lane);
+                sv = __ldg(p.logit + base + lane);
             }
-            float w_keep = 0.f, ds_keep = 0.f;  // lane k keeps the record of edge base+k
-            int k = 0;
-            for (; k < cnt; k += U) {
-                Row<VPL> q[U], x[U], s[U], r[U];
+            float w_keep = 0.f, ds_keep = 0.f;      // lane k keeps the record of edge base+k
+            for (int k = 0; k < cnt; k += U) {
+                Row<VPL> x[U], r[U];
+                unsigned bits[U];
+                float sc[U], uu[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int kk = min(k + u, cnt - 1);  // clamp: tail edges are recomputed, never recorded twice
+                    const int kk = min(k + u, cnt - 1);     // clamp: tail edges are recomputed, never recorded twice
                     const int j = __shfl_sync(FULL, jv, kk);
                     const int t = __shfl_sync(FULL, tv, kk);
-                    load_row<VPL, true>(q[u], p.Q, j, d4, lane);
+                    sc[u] = __shfl_sync(FULL, sv, kk);
                     load_row<VPL, true>(x[u], p.X, j, d4, lane);
-                    load_row<VPL, false>(s[u], p.S, t, d4, lane);
                     load_row<VPL, false>(r[u], p.Rp, t, d4, lane);
+                    bits[u] = (unsigned)maskp[(size_t)(base + kk) * 32 + lane];
                 }
-                float sc[U], uu[U];
-                unsigned bits[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    sc[u] = 0.f; uu[u] = 0.f; bits[u] = 0u;
+                    uu[u] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < VPL; ++i) {
-                        float4 z = pi.v[i] + q[u].v[i] - s[u].v[i];
-                        bits[u] |= ((z.x > 0.f ? 1u : 0u) | (z.y > 0.f ? 2u : 0u) | (z.z > 0.f ? 4u : 0u) | (z.w > 0.f ? 8u : 0u)) << (4 * i);
-                        z.x = z.x > 0.f ? z.x : p.slope * z.x;
-                        z.y = z.y > 0.f ? z.y : p.slope * z.y;
-                        z.z = z.z > 0.f ? z.z : p.slope * z.z;
-                        z.w = z.w > 0.f ? z.w : p.slope * z.w;
-                        sc[u] += dot4(av.v[i], z);
-                        uu[u] += dot4(gi.v[i], x[u].v[i] - r[u].v[i]);
-                        q[u].v[i] = z;  // keep LeakyReLU(z) for da_att
-                    }
+                    for (int i = 0; i < VPL; ++i) uu[u] += dot4(gi.v[i], x[u].v[i] - r[u].v[i]);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        sc[u] += __shfl_xor_sync(FULL, sc[u], o);
-                        uu[u] += __shfl_xor_sync(FULL, uu[u], o);
-                    }
+                    for (int u = 0; u < U; ++u) uu[u] += __shfl_xor_sync(FULL, uu[u], o);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (k + u < cnt) {  // warp-uniform
+                    if (k + u < cnt) {                      // warp-uniform
                         const float alpha = __expf(sc[u] - lse);
                         const float w = c * alpha;
                         const float ds = alpha * (c * uu[u] - gdot);
-                        const float dsl = ds * p.slope;
+                        ds_sum += ds;
 #pragma unroll
                         for (int i = 0; i < VPL; ++i) {
                             const unsigned b = bits[u] >> (4 * i);
-                            dp_acc.v[i].x = fmaf((b & 1u) ? ds : dsl, av.v[i].x, dp_acc.v[i].x);
-                            dp_acc.v[i].y = fmaf((b & 2u) ? ds : dsl, av.v[i].y, dp_acc.v[i].y);
-                            dp_acc.v[i].z = fmaf((b & 4u) ? ds : dsl, av.v[i].z, dp_acc.v[i].z);
-                            dp_acc.v[i].w = fmaf((b & 8u) ? ds : dsl, av.v[i].w, dp_acc.v[i].w);
-                            fma4(da_acc.v[i], ds, q[u].v[i]);
+                            mu.v[i].x += (b & 1u) ? ds : 0.f;
+                            mu.v[i].y += (b & 2u) ? ds : 0.f;
+                            mu.v[i].z += (b & 4u) ? ds : 0.f;
+                            mu.v[i].w += (b & 8u) ? ds : 0.f;
                         }
-                        maskp[(size_t)(base + k + u) * 32 + lane] = (mask_t)bits[u];
                         if (lane == k + u) { w_keep = w; ds_keep = ds; }
                     }
                 }
             }
             if (lane < cnt) p.ew[base + lane] = make_float2(w_keep, ds_keep);
         }
-        if (item.slot < 0) store_row<VPL>(dp_acc, p.dP, item.seg, d4, lane);
-        else store_row<VPL>(dp_acc, p.partial, item.slot, d4, lane);
-    }
-    // da_att: block-level reduction in shared memory, then one RED per feature per block
-    __shared__ float4 red[8][VPL * 32];
-    const int wib = threadIdx.x >> 5;
+        // mu' = slope * sum ds + (1 - slope) * sum_{z>0} ds;  dP = a (.) mu';  d a += P[i] (.) mu'
+        const float lo = p.slope * ds_sum;
+        Row<VPL> pi;
+        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) red[wib][i * 32 + lane] = da_acc.v[i];
-    __syncthreads();
-    for (int c4 = threadIdx.x; c4 < d4; c4 += blockDim.x) {
-        float4 s = red[0][c4];
-        for (int w = 1; w < 8; ++w) s = s + red[w][c4];
-        red_add_v4(p.da + 4 * c4, s);
+        for (int i = 0; i < VPL; ++i) {
+            mu.v[i].x = fmaf(hi, mu.v[i].x, lo); mu.v[i].y = fmaf(hi, mu.v[i].y, lo);
+            mu.v[i].z = fmaf(hi, mu.v[i].z, lo); mu.v[i].w = fmaf(hi, mu.v[i].w, lo);
+            da_acc.v[i].x = fmaf(pi.v[i].x, mu.v[i].x, da_acc.v[i].x); da_acc.v[i].y = fmaf(pi.v[i].y, mu.v[i].y, da_acc.v[i].y);
+            da_acc.v[i].z = fmaf(pi.v[i].z, mu.v[i].z, da_acc.v[i].z); da_acc.v[i].w = fmaf(pi.v[i].w, mu.v[i].w, da_acc.v[i].w);
+            mu.v[i].x *= av.v[i].x; mu.v[i].y *= av.v[i].y; mu.v[i].z *= av.v[i].z; mu.v[i].w *= av.v[i].w;
+        }
+        if (item.slot < 0) store_row<VPL>(mu, p.dP, item.seg, d4, lane);
+        else store_row<VPL>(mu, p.partial, item.slot, d4, lane);
     }
+    flush_da<VPL>(da_acc, p.da, d4);
 }
 
 // Sum of the partial rows of split segments: out[seg] = sum_k partial[first + k]; `rows` rows per slot.
@@ -178,17 +185,19 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const Split* __restri
 struct EdgeBwdGatherParams {
     const Item* items;
     int n_items;
-    const int* pos;   // ordering position -> CSR position
-    const int* dst;   // ordering position -> destination node
+    const int* pos;    // ordering position -> CSR position
+    const int* dst;    // ordering position -> destination node
     const float* G;
     const float2* ew;
     const void* mask;
     const float* a;
+    const float* Z;    // Q (src pass, rows = sources) or S (rel pass, rows = relations): the d a_att term
     float slope;
     int d4;
-    float* out_w;     // sum w_e G[i]      (dXe for the src pass, dR' for the rel pass)
-    float* out_z;     // sum d z_e         (dQ  for the src pass, dS  for the rel pass)
-    float* partial;   // [n_slots, 2, d]   (src pass only)
+    float* out_w;      // sum w_e G[i]      (dXe for the src pass, dR' for the rel pass)
+    float* out_z;      // sum d z_e         (dQ  for the src pass, dS  for the rel pass)
+    float* da;         // [d] accumulated
+    float* partial;    // [n_slots, 2, d]   (src pass only)
 };
 
 // MODE 0: source pass (rows written / partials); MODE 1: relation pass (negated; split segments RED
@@ -200,8 +209,9 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int d4 = p.d4;
-    Row<VPL> av;
+    Row<VPL> av, da_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
+    da_acc.zero();
     const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
     const float sign = MODE == 0 ? 1.f : -1.f;
 
@@ -252,14 +262,17 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
                 }
             }
         }
-        // d z summed = a (.) (slope * sum ds + (1 - slope) * sum_{z>0} ds)
+        // nu' = slope * sum ds + (1 - slope) * sum_{z>0} ds;  d a += sign * Z[seg] (.) nu';  out_z = sign * a (.) nu'
         const float lo = p.slope * ds_sum, hi = 1.f - p.slope;
+        Row<VPL> zr;
+        load_row<VPL, MODE == 0>(zr, p.Z, item.seg, d4, lane);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            accz.v[i].x = sign * av.v[i].x * fmaf(hi, accz.v[i].x, lo);
-            accz.v[i].y = sign * av.v[i].y * fmaf(hi, accz.v[i].y, lo);
-            accz.v[i].z = sign * av.v[i].z * fmaf(hi, accz.v[i].z, lo);
-            accz.v[i].w = sign * av.v[i].w * fmaf(hi, accz.v[i].w, lo);
+            accz.v[i].x = sign * fmaf(hi, accz.v[i].x, lo); accz.v[i].y = sign * fmaf(hi, accz.v[i].y, lo);
+            accz.v[i].z = sign * fmaf(hi, accz.v[i].z, lo); accz.v[i].w = sign * fmaf(hi, accz.v[i].w, lo);
+            da_acc.v[i].x = fmaf(zr.v[i].x, accz.v[i].x, da_acc.v[i].x); da_acc.v[i].y = fmaf(zr.v[i].y, accz.v[i].y, da_acc.v[i].y);
+            da_acc.v[i].z = fmaf(zr.v[i].z, accz.v[i].z, da_acc.v[i].z); da_acc.v[i].w = fmaf(zr.v[i].w, accz.v[i].w, da_acc.v[i].w);
+            accz.v[i].x *= av.v[i].x; accz.v[i].y *= av.v[i].y; accz.v[i].z *= av.v[i].z; accz.v[i].w *= av.v[i].w;
             accw.v[i] = sign * accw.v[i];
         }
         if (item.slot < 0) {
@@ -279,29 +292,297 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
             }
         }
     }
+    flush_da<VPL>(da_acc, p.da, d4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ring variants (default): the one gathered node row per edge (X[j] in the dst pass, G[i] in the src / rel
+// passes) is fetched by lane 0 with cp.async.bulk into a per-warp ring of shared-memory slots, BWD_RING_S-1
+// edges ahead of its use, two edges are consumed per iteration.  16 warps x 12 slots x 1 KB = 192 KB of
+// gathers in flight per SM (d = 256) -- the register-staged kernels above top out at ~64 KB, which Little's
+// law (2-2.7 us loaded latency) turns into ~4.5 TB/s.
+// ------------------------------------------------------------------------------------------------
+constexpr int BWD_RING_S = 12;
+
+struct Ring {
+    float* slots;
+    uint32_t slots_s, bars, row_bytes;
+    int row_f;
+    uint32_t cnt_issue, cnt_use;
+    __device__ __forceinline__ void init(uint8_t* raw, int wib, int lane, int d4) {
+        row_bytes = (uint32_t)d4 * 16;
+        row_f = d4 * 4;
+        slots = reinterpret_cast<float*>(raw) + (size_t)wib * BWD_RING_S * row_f;
+        slots_s = smem_addr(slots);
+        bars = smem_addr(raw) + (uint32_t)RING_WARPS * BWD_RING_S * row_bytes + (uint32_t)wib * BWD_RING_S * 8;
+        cnt_issue = cnt_use = 0;
+        if (lane == 0) {
+            for (int s = 0; s < BWD_RING_S; ++s) mbar_init(bars + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void issue(const float* table, int row, int lane) {
+        if (lane == 0) {
+            const uint32_t s = cnt_issue % BWD_RING_S;
+            mbar_expect_tx(bars + 8 * s, row_bytes);
+            bulk_row(slots_s + s * row_bytes, table + (size_t)row * row_f, row_bytes, bars + 8 * s);
+        }
+        ++cnt_issue;
+    }
+    // waits for the next slot in consumption order and returns its shared-memory row
+    __device__ __forceinline__ const float* wait_next() {
+        const uint32_t s = cnt_use % BWD_RING_S;
+        mbar_wait(bars + 8 * s, (cnt_use / BWD_RING_S) & 1);
+        ++cnt_use;
+        return slots + (size_t)s * row_f;
+    }
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(EdgeBwdDstParams p) {
+    typedef typename MaskT<VPL>::type mask_t;
+    extern __shared__ __align__(16) uint8_t ring_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * RING_WARPS + wib;
+    const int nwarps = gridDim.x * RING_WARPS;
+    const int d4 = p.d4;
+    Ring ring;
+    ring.init(ring_raw, wib, lane, d4);
+    Row<VPL> av, da_acc;
+    load_row<VPL, false>(av, p.a, 0, d4, lane);
+    da_acc.zero();
+    const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
+    const float hi = 1.f - p.slope;
+    constexpr int ADV = (32 - BWD_RING_S) & ~1;
+
+    for (int it = warp; it < p.n_items; it += nwarps) {
+        const Item item = p.items[it];
+        const int n = item.end - item.beg;
+        Row<VPL> gi, mu;
+        load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
+        mu.zero();
+        float gdot = 0.f, ds_sum = 0.f;
+        {
+            Row<VPL> ai;
+            load_row<VPL, true>(ai, p.agg, item.seg, d4, lane);
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) gdot += dot4(gi.v[i], ai.v[i]);
+            gdot = warp_sum(gdot);
+        }
+        const float lse = p.lse[item.seg];
+        const float c = p.sqrt_deg[item.seg];
+        int issued = 0;
+        for (int base = 0; base < n; base += ADV) {
+            int jv = 0, tv = 0;
+            float sv = 0.f;
+            if (base + lane < n) {
+                jv = __ldg(p.csr_src + item.beg + base + lane);
+                tv = __ldg(p.csr_type + item.beg + base + lane);
+                sv = __ldg(p.logit + item.beg + base + lane);
+            }
+            float w_keep = 0.f, ds_keep = 0.f;
+            const int lim = min(n, base + ADV);
+            for (int k = base; k < lim; k += 2) {
+                const int want = min(n, k + BWD_RING_S);
+                while (issued < want) {                              // warp-uniform
+                    ring.issue(p.X, __shfl_sync(FULL, jv, issued - base), lane);
+                    ++issued;
+                }
+                const bool two = k + 1 < lim;
+                const int k1 = two ? k + 1 : k;
+                const int t0 = __shfl_sync(FULL, tv, k - base), t1 = __shfl_sync(FULL, tv, k1 - base);
+                const float sc0 = __shfl_sync(FULL, sv, k - base), sc1 = __shfl_sync(FULL, sv, k1 - base);
+                Row<VPL> r0, r1;
+                load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
+                load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
+                const unsigned b0 = (unsigned)maskp[(size_t)(item.beg + k) * 32 + lane];
+                const unsigned b1 = (unsigned)maskp[(size_t)(item.beg + k1) * 32 + lane];
+                Row<VPL> x0, x1;
+                const float* sl0 = ring.wait_next();
+                lds_row<VPL>(x0, sl0, d4, lane);
+                if (two) {
+                    const float* sl1 = ring.wait_next();
+                    lds_row<VPL>(x1, sl1, d4, lane);
+                } else {
+                    x1 = x0;
+                }
+                __syncwarp();                                        // slots may be refilled
+                float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    u0 += dot4(gi.v[i], x0.v[i] - r0.v[i]);
+                    u1 += dot4(gi.v[i], x1.v[i] - r1.v[i]);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    u0 += __shfl_xor_sync(FULL, u0, o);
+                    u1 += __shfl_xor_sync(FULL, u1, o);
+                }
+                const float al0 = __expf(sc0 - lse), al1 = two ? __expf(sc1 - lse) : 0.f;
+                const float ds0 = al0 * (c * u0 - gdot), ds1 = al1 * (c * u1 - gdot);
+                ds_sum += ds0 + ds1;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const unsigned q0 = b0 >> (4 * i), q1 = b1 >> (4 * i);
+                    mu.v[i].x += ((q0 & 1u) ? ds0 : 0.f) + ((q1 & 1u) ? ds1 : 0.f);
+                    mu.v[i].y += ((q0 & 2u) ? ds0 : 0.f) + ((q1 & 2u) ? ds1 : 0.f);
+                    mu.v[i].z += ((q0 & 4u) ? ds0 : 0.f) + ((q1 & 4u) ? ds1 : 0.f);
+                    mu.v[i].w += ((q0 & 8u) ? ds0 : 0.f) + ((q1 & 8u) ? ds1 : 0.f);
+                }
+                if (lane == k - base) { w_keep = c * al0; ds_keep = ds0; }
+                if (two && lane == k + 1 - base) { w_keep = c * al1; ds_keep = ds1; }
+            }
+            if (base + lane < lim) p.ew[item.beg + base + lane] = make_float2(w_keep, ds_keep);
+        }
+        const float lo = p.slope * ds_sum;
+        Row<VPL> pi;
+        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            mu.v[i].x = fmaf(hi, mu.v[i].x, lo); mu.v[i].y = fmaf(hi, mu.v[i].y, lo);
+            mu.v[i].z = fmaf(hi, mu.v[i].z, lo); mu.v[i].w = fmaf(hi, mu.v[i].w, lo);
+            da_acc.v[i].x = fmaf(pi.v[i].x, mu.v[i].x, da_acc.v[i].x); da_acc.v[i].y = fmaf(pi.v[i].y, mu.v[i].y, da_acc.v[i].y);
+            da_acc.v[i].z = fmaf(pi.v[i].z, mu.v[i].z, da_acc.v[i].z); da_acc.v[i].w = fmaf(pi.v[i].w, mu.v[i].w, da_acc.v[i].w);
+            mu.v[i].x *= av.v[i].x; mu.v[i].y *= av.v[i].y; mu.v[i].z *= av.v[i].z; mu.v[i].w *= av.v[i].w;
+        }
+        if (item.slot < 0) store_row<VPL>(mu, p.dP, item.seg, d4, lane);
+        else store_row<VPL>(mu, p.partial, item.slot, d4, lane);
+    }
+    flush_da16<VPL>(da_acc, p.da, d4);
+}
+
+template <int VPL, int MODE>
+__global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kernel(EdgeBwdGatherParams p) {
+    typedef typename MaskT<VPL>::type mask_t;
+    extern __shared__ __align__(16) uint8_t ring_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * RING_WARPS + wib;
+    const int nwarps = gridDim.x * RING_WARPS;
+    const int d4 = p.d4;
+    Ring ring;
+    ring.init(ring_raw, wib, lane, d4);
+    Row<VPL> av, da_acc;
+    load_row<VPL, false>(av, p.a, 0, d4, lane);
+    da_acc.zero();
+    const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
+    const float sign = MODE == 0 ? 1.f : -1.f;
+    constexpr int ADV = (32 - BWD_RING_S) & ~1;
+
+    for (int it = warp; it < p.n_items; it += nwarps) {
+        const Item item = p.items[it];
+        const int n = item.end - item.beg;
+        Row<VPL> accw, accz;
+        accw.zero();
+        accz.zero();
+        float ds_sum = 0.f;
+        int issued = 0;
+        for (int base = 0; base < n; base += ADV) {
+            int pv = 0, iv = 0;
+            float2 e2 = make_float2(0.f, 0.f);
+            if (base + lane < n) {
+                pv = __ldg(p.pos + item.beg + base + lane);
+                iv = __ldg(p.dst + item.beg + base + lane);
+                e2 = __ldg(p.ew + pv);
+            }
+            const int lim = min(n, base + ADV);
+            for (int k = base; k < lim; k += 2) {
+                const int want = min(n, k + BWD_RING_S);
+                while (issued < want) {                              // warp-uniform
+                    ring.issue(p.G, __shfl_sync(FULL, iv, issued - base), lane);
+                    ++issued;
+                }
+                const bool two = k + 1 < lim;
+                const int k1 = two ? k + 1 : k;
+                const int pp0 = __shfl_sync(FULL, pv, k - base), pp1 = __shfl_sync(FULL, pv, k1 - base);
+                const float w0 = __shfl_sync(FULL, e2.x, k - base), d0 = __shfl_sync(FULL, e2.y, k - base);
+                float w1 = __shfl_sync(FULL, e2.x, k1 - base), d1 = __shfl_sync(FULL, e2.y, k1 - base);
+                if (!two) { w1 = 0.f; d1 = 0.f; }
+                const unsigned b0 = (unsigned)maskp[(size_t)pp0 * 32 + lane];
+                const unsigned b1 = (unsigned)maskp[(size_t)pp1 * 32 + lane];
+                Row<VPL> g0, g1;
+                const float* sl0 = ring.wait_next();
+                lds_row<VPL>(g0, sl0, d4, lane);
+                if (two) {
+                    const float* sl1 = ring.wait_next();
+                    lds_row<VPL>(g1, sl1, d4, lane);
+                } else {
+                    g1 = g0;
+                }
+                __syncwarp();
+                ds_sum += d0 + d1;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    fma4(accw.v[i], w0, g0.v[i]);
+                    fma4(accw.v[i], w1, g1.v[i]);
+                    const unsigned q0 = b0 >> (4 * i), q1 = b1 >> (4 * i);
+                    accz.v[i].x += ((q0 & 1u) ? d0 : 0.f) + ((q1 & 1u) ? d1 : 0.f);
+                    accz.v[i].y += ((q0 & 2u) ? d0 : 0.f) + ((q1 & 2u) ? d1 : 0.f);
+                    accz.v[i].z += ((q0 & 4u) ? d0 : 0.f) + ((q1 & 4u) ? d1 : 0.f);
+                    accz.v[i].w += ((q0 & 8u) ? d0 : 0.f) + ((q1 & 8u) ? d1 : 0.f);
+                }
+            }
+        }
+        const float lo = p.slope * ds_sum, hi = 1.f - p.slope;
+        Row<VPL> zr;
+        load_row<VPL, MODE == 0>(zr, p.Z, item.seg, d4, lane);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            accz.v[i].x = sign * fmaf(hi, accz.v[i].x, lo); accz.v[i].y = sign * fmaf(hi, accz.v[i].y, lo);
+            accz.v[i].z = sign * fmaf(hi, accz.v[i].z, lo); accz.v[i].w = sign * fmaf(hi, accz.v[i].w, lo);
+            da_acc.v[i].x = fmaf(zr.v[i].x, accz.v[i].x, da_acc.v[i].x); da_acc.v[i].y = fmaf(zr.v[i].y, accz.v[i].y, da_acc.v[i].y);
+            da_acc.v[i].z = fmaf(zr.v[i].z, accz.v[i].z, da_acc.v[i].z); da_acc.v[i].w = fmaf(zr.v[i].w, accz.v[i].w, da_acc.v[i].w);
+            accz.v[i].x *= av.v[i].x; accz.v[i].y *= av.v[i].y; accz.v[i].z *= av.v[i].z; accz.v[i].w *= av.v[i].w;
+            accw.v[i] = sign * accw.v[i];
+        }
+        if (item.slot < 0) {
+            store_row<VPL>(accw, p.out_w, item.seg, d4, lane);
+            store_row<VPL>(accz, p.out_z, item.seg, d4, lane);
+        } else if (MODE == 0) {
+            store_row<VPL>(accw, p.partial, (int64_t)item.slot * 2, d4, lane);
+            store_row<VPL>(accz, p.partial, (int64_t)item.slot * 2 + 1, d4, lane);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int c = i * 32 + lane;
+                if (c < d4) {
+                    red_add_v4(p.out_w + ((size_t)item.seg * d4 + c) * 4, accw.v[i]);
+                    red_add_v4(p.out_z + ((size_t)item.seg * d4 + c) * 4, accz.v[i]);
+                }
+            }
+        }
+    }
+    flush_da16<VPL>(da_acc, p.da, d4);
+}
+
+static inline size_t bwd_ring_smem(int d) { return (size_t)RING_WARPS * BWD_RING_S * ((size_t)d * 4 + 8); }
+static inline bool use_ring(int d) {
+    static const int on = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
+    return on && bwd_ring_smem(d) <= 220 * 1024;
 }
 
 }  // namespace jmac
 
 using namespace jmac;
 
-extern "C" size_t jmac_edge_record_bytes(int d) { return dim_ok(d) ? 8 + mask_bytes(d) : 0; }
+extern "C" size_t jmac_edge_record_bytes(int d) { return dim_ok(d) ? 8 + edge_mask_bytes(d) + 4 : 0; }
 
-extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S, const float* Rp,
-                                 const float* a_att, float leaky_slope, int d, const float* agg, const float* lse, const float* G,
-                                 float* dP, void* erec, float* da_att, void* stream) {
-    JMAC_ARG(plan && P && Q && X && S && Rp && a_att && agg && lse && G && dP && da_att);
+extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X, const float* Rp, const float* a_att, float leaky_slope,
+                                 int d, const float* agg, const float* lse, const float* G, float* dP, void* erec, float* da_att,
+                                 void* stream) {
+    JMAC_ARG(plan && P && X && Rp && a_att && agg && lse && G && dP && da_att);
     JMAC_ARG(plan->E == 0 || erec != nullptr);
     JMAC_ARG(dim_ok(d));
     cudaStream_t st = (cudaStream_t)stream;
     EdgeBwdDstParams p;
     p.items = plan->dst_items.items; p.n_items = plan->dst_items.n_items;
     p.csr_src = plan->csr_src; p.csr_type = plan->csr_type; p.sqrt_deg = plan->sqrt_deg;
-    p.P = P; p.Q = Q; p.X = X; p.S = S; p.Rp = Rp; p.a = a_att;
+    p.P = P; p.X = X; p.Rp = Rp; p.a = a_att;
     p.slope = leaky_slope; p.d4 = d / 4;
     p.agg = agg; p.lse = lse; p.G = G; p.dP = dP;
-    p.ew = reinterpret_cast<float2*>(erec);
-    p.mask = reinterpret_cast<char*>(erec) + sizeof(float2) * (size_t)plan->E;
+    p.ew = erec_ew(erec);
+    p.mask = erec_mask(erec, plan->E);
+    p.logit = erec_logit(erec, plan->E, d);
     p.da = da_att;
     p.partial = nullptr;
     if (plan->dst_items.n_slots > 0) {
@@ -311,10 +592,17 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* Q
     if (p.n_items == 0) return 0;
     const int threads = 256;
     JMAC_DISPATCH_VPL(d, {
-        constexpr int U = VPL == 1 ? 4 : 2;
-        auto kern = edge_bwd_dst_kernel<VPL, U>;
-        int blocks = persistent_blocks(kern, threads, p.n_items);
-        kern<<<blocks, threads, 0, st>>>(p);
+        constexpr int U = VPL <= 2 ? 4 : 2;
+        if (use_ring(d)) {
+            auto kern = edge_bwd_dst_ring_kernel<VPL>;
+            JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
+            long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
+            kern<<<(int)(want < sm_count() ? want : sm_count()), RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
+        } else {
+            auto kern = edge_bwd_dst_kernel<VPL, U>;
+            int blocks = persistent_blocks(kern, threads, p.n_items);
+            kern<<<blocks, threads, 0, st>>>(p);
+        }
         JMAC_LAUNCH_CHECK();
         if (plan->dst_items.n_splits > 0) {
             int mb = (plan->dst_items.n_splits * 32 + threads - 1) / threads;
@@ -325,9 +613,9 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* Q
     return 0;
 }
 
-static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* erec, const float* a_att, float slope, int d,
-                       float* out_w, float* out_z, cudaStream_t st) {
-    JMAC_ARG(plan && G && a_att && out_w && out_z);
+static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* erec, const float* a_att, float slope, int d, const float* Z,
+                       float* out_w, float* out_z, float* da_att, cudaStream_t st) {
+    JMAC_ARG(plan && G && a_att && Z && out_w && out_z && da_att);
     JMAC_ARG(plan->E == 0 || erec != nullptr);
     JMAC_ARG(dim_ok(d));
     const ItemList& il = mode == 0 ? plan->src_items : plan->typ_items;
@@ -336,10 +624,10 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
     p.pos = mode == 0 ? plan->csc_pos : plan->typ_pos;
     p.dst = mode == 0 ? plan->csc_dst : plan->typ_dst;
     p.G = G;
-    p.ew = reinterpret_cast<const float2*>(erec);
-    p.mask = reinterpret_cast<const char*>(erec) + sizeof(float2) * (size_t)plan->E;
-    p.a = a_att; p.slope = slope; p.d4 = d / 4;
-    p.out_w = out_w; p.out_z = out_z;
+    p.ew = erec_ew(const_cast<void*>(erec));
+    p.mask = erec_mask(const_cast<void*>(erec), plan->E);
+    p.a = a_att; p.Z = Z; p.slope = slope; p.d4 = d / 4;
+    p.out_w = out_w; p.out_z = out_z; p.da = da_att;
     p.partial = nullptr;
     if (mode == 1) {
         JMAC_CUDA(cudaMemsetAsync(out_w, 0, sizeof(float) * (size_t)plan->n_rel * d, st));
@@ -352,10 +640,19 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
     const int threads = 256;
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL == 1 ? 4 : (VPL == 2 ? 4 : 2);
+        const bool ring = use_ring(d);
+        const long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
+        const int rblocks = (int)(want < sm_count() ? want : sm_count());
         if (mode == 0) {
-            auto kern = edge_bwd_gather_kernel<VPL, 0, U>;
-            int blocks = persistent_blocks(kern, threads, p.n_items);
-            kern<<<blocks, threads, 0, st>>>(p);
+            if (ring) {
+                auto kern = edge_bwd_gather_ring_kernel<VPL, 0>;
+                JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
+                kern<<<rblocks, RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
+            } else {
+                auto kern = edge_bwd_gather_kernel<VPL, 0, U>;
+                int blocks = persistent_blocks(kern, threads, p.n_items);
+                kern<<<blocks, threads, 0, st>>>(p);
+            }
             JMAC_LAUNCH_CHECK();
             if (il.n_splits > 0) {
                 int mb = (il.n_splits * 32 + threads - 1) / threads;
@@ -363,9 +660,15 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
                 JMAC_LAUNCH_CHECK();
             }
         } else {
-            auto kern = edge_bwd_gather_kernel<VPL, 1, U>;
-            int blocks = persistent_blocks(kern, threads, p.n_items);
-            kern<<<blocks, threads, 0, st>>>(p);
+            if (ring) {
+                auto kern = edge_bwd_gather_ring_kernel<VPL, 1>;
+                JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
+                kern<<<rblocks, RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
+            } else {
+                auto kern = edge_bwd_gather_kernel<VPL, 1, U>;
+                int blocks = persistent_blocks(kern, threads, p.n_items);
+                kern<<<blocks, threads, 0, st>>>(p);
+            }
             JMAC_LAUNCH_CHECK();
         }
     });
@@ -373,11 +676,11 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
 }
 
 extern "C" int jmac_edge_bwd_src(jmac_plan* plan, const float* G, const void* erec, const float* a_att, float leaky_slope, int d,
-                                 float* dXe, float* dQ, void* stream) {
-    return gather_pass(plan, 0, G, erec, a_att, leaky_slope, d, dXe, dQ, (cudaStream_t)stream);
+                                 const float* Q, float* dXe, float* dQ, float* da_att, void* stream) {
+    return gather_pass(plan, 0, G, erec, a_att, leaky_slope, d, Q, dXe, dQ, da_att, (cudaStream_t)stream);
 }
 
 extern "C" int jmac_edge_bwd_rel(jmac_plan* plan, const float* G, const void* erec, const float* a_att, float leaky_slope, int d,
-                                 float* dRp, float* dS, void* stream) {
-    return gather_pass(plan, 1, G, erec, a_att, leaky_slope, d, dRp, dS, (cudaStream_t)stream);
+                                 const float* S, float* dRp, float* dS, float* da_att, void* stream) {
+    return gather_pass(plan, 1, G, erec, a_att, leaky_slope, d, S, dRp, dS, da_att, (cudaStream_t)stream);
 }

@@ -33,6 +33,9 @@ struct EdgeFwdParams {
     const float* Xself;
     const float* loop_row;
     float* T;
+    // optional per-edge record for backward (both null when no gradient is needed)
+    void* mask;      // [E][32 lanes] sign mask of z_e
+    float* logit;    // [E] attention logit s_e
 };
 
 // T = agg + X[i] - R'[loop]: the operand of the message GEMM ((neigh + self) W_g, src/jmac_model.py:49-52)
@@ -47,11 +50,14 @@ __device__ __forceinline__ void store_self_fused(const EdgeFwdParams& p, const R
 }
 
 template <int VPL>
-__device__ __forceinline__ float leaky_dot(const Row<VPL>& pi, const Row<VPL>& q, const Row<VPL>& s, const Row<VPL>& a, float slope) {
+__device__ __forceinline__ float leaky_dot(const Row<VPL>& pi, const Row<VPL>& q, const Row<VPL>& s, const Row<VPL>& a, float slope,
+                                           unsigned& bits) {
     float part = 0.f;
+    bits = 0u;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         float4 z = pi.v[i] + q.v[i] - s.v[i];
+        bits |= ((z.x > 0.f ? 1u : 0u) | (z.y > 0.f ? 2u : 0u) | (z.z > 0.f ? 4u : 0u) | (z.w > 0.f ? 8u : 0u)) << (4 * i);
         z.x = z.x > 0.f ? z.x : slope * z.x;
         z.y = z.y > 0.f ? z.y : slope * z.y;
         z.z = z.z > 0.f ? z.z : slope * z.z;
@@ -61,12 +67,27 @@ __device__ __forceinline__ float leaky_dot(const Row<VPL>& pi, const Row<VPL>& q
     return part;
 }
 
+// Sign mask of one edge: lane l owns the (VPL <= 2 ? 1 : 2) bytes at offset l of the edge's 32/64-byte record.
+// Packed through two (one) shuffles so that 8 (16) lanes issue 32-bit stores instead of 32 byte stores.
+template <int VPL>
+__device__ __forceinline__ void store_mask(void* mask, int edge, unsigned bits, int lane) {
+    if (VPL <= 2) {
+        unsigned v = bits | (__shfl_down_sync(FULL, bits, 1) << 8);
+        v |= __shfl_down_sync(FULL, v, 2) << 16;
+        if ((lane & 3) == 0) reinterpret_cast<unsigned*>(mask)[(size_t)edge * 8 + (lane >> 2)] = v;
+    } else {
+        const unsigned v = bits | (__shfl_down_sync(FULL, bits, 1) << 16);
+        if ((lane & 1) == 0) reinterpret_cast<unsigned*>(mask)[(size_t)edge * 16 + (lane >> 1)] = v;
+    }
+}
+
 template <int VPL, int U>
 __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int d4 = p.d4;
+    const bool save = p.logit != nullptr;
     Row<VPL> av;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
 
@@ -84,6 +105,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
                 jv = __ldg(p.csr_src + base + lane);
                 tv = __ldg(p.csr_type + base + lane);
             }
+            float sc_keep = 0.f;                      // lane k keeps the logit of edge base+k
             int k = 0;
             for (; k + U <= cnt; k += U) {
                 Row<VPL> q[U], x[U], s[U], r[U];
@@ -97,12 +119,20 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
                     load_row<VPL, false>(r[u], p.Rp, t, d4, lane);
                 }
                 float sc[U];
+                unsigned bits[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) sc[u] = leaky_dot<VPL>(pi, q[u], s[u], av, p.slope);
+                for (int u = 0; u < U; ++u) sc[u] = leaky_dot<VPL>(pi, q[u], s[u], av, p.slope, bits[u]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(FULL, sc[u], o);
+                }
+                if (save) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        store_mask<VPL>(p.mask, base + k + u, bits[u], lane);
+                        if (lane == k + u) sc_keep = sc[u];
+                    }
                 }
                 float mn = m;
 #pragma unroll
@@ -128,7 +158,12 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
                 load_row<VPL, true>(x, p.X, j, d4, lane);
                 load_row<VPL, false>(s, p.S, t, d4, lane);
                 load_row<VPL, false>(r, p.Rp, t, d4, lane);
-                const float sc = warp_sum(leaky_dot<VPL>(pi, q, s, av, p.slope));
+                unsigned bits1;
+                const float sc = warp_sum(leaky_dot<VPL>(pi, q, s, av, p.slope, bits1));
+                if (save) {
+                    store_mask<VPL>(p.mask, base + k, bits1, lane);
+                    if (lane == k) sc_keep = sc;
+                }
                 const float mn = fmaxf(m, sc);
                 const float corr = __expf(m - mn);
                 const float pe = __expf(sc - mn);
@@ -140,6 +175,7 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
                 }
                 m = mn;
             }
+            if (save && lane < cnt) p.logit[base + lane] = sc_keep;
         }
         if (item.slot < 0) {
             const float c = p.sqrt_deg[item.seg];
@@ -165,36 +201,15 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
 // (12 warps x 7 slots x 2 KB per SM) instead of by occupancy; the LSU only sees conflict-free LDS.128.
 // The relation rows S[t], R'[t] are L2-resident: plain loads, prefetched one edge ahead in registers.
 // ------------------------------------------------------------------------------------------------
-constexpr int RING_WARPS = 12, RING_S = 8, RING_ROWS = 2;   // slot = {Q[j], X[j]}
+constexpr int RING_S = 6, RING_ROWS = 2;   // slot = {Q[j], X[j]}; 16 warps x 6 x 2 KB = 192 KB at d = 256
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
-                 : "memory");
-}
-
+// one edge of the ring: logit from the shared-memory copies of Q[j] (row 0 of the slot) and the relation row S[t]
 template <int VPL>
-__device__ __forceinline__ void lds_row(Row<VPL>& r, const float* base, int d4, int lane) {
-    const float4* p = reinterpret_cast<const float4*>(base);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int c = i * 32 + lane;
-        r.v[i] = c < d4 ? p[c] : f4_zero();
-    }
+__device__ __forceinline__ float ring_logit(const Row<VPL>& pi, const float* slot, const Row<VPL>& sr, const Row<VPL>& av, float slope,
+                                            int d4, int lane, unsigned& bits) {
+    Row<VPL> q;
+    lds_row<VPL>(q, slot, d4, lane);
+    return leaky_dot<VPL>(pi, q, sr, av, slope, bits);
 }
 
 template <int VPL>
@@ -214,6 +229,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const bool save = p.logit != nullptr;
     Row<VPL> av;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     uint32_t cnt_issue = 0, cnt_use = 0;                          // edges issued / consumed by this warp so far
@@ -226,24 +242,19 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
         float m = -INFINITY, l = 0.f;
         Row<VPL> acc;
         acc.zero();
-        // indices are fetched 32 at a time but consumed 32 - RING_S at a time, so that the edge being
-        // issued (RING_S - 1 ahead of the one being consumed) is always inside the current batch
-        constexpr int ADV = 32 - RING_S;
+        // indices are fetched 32 at a time but consumed ADV at a time, so that the edge being issued
+        // (up to RING_S - 1 ahead of the one being consumed) is always inside the current batch
+        constexpr int ADV = (32 - RING_S) & ~1;
         int issued = 0;
-        Row<VPL> sn, rn;                                           // relation rows of the NEXT edge (L2-resident: register prefetch)
         for (int base = 0; base < n; base += ADV) {
             int jv = 0, tv = 0;
             if (base + lane < n) {
                 jv = __ldg(p.csr_src + item.beg + base + lane);
                 tv = __ldg(p.csr_type + item.beg + base + lane);
             }
-            if (base == 0) {
-                const int t0 = __shfl_sync(FULL, tv, 0);
-                load_row<VPL, false>(sn, p.S, t0, d4, lane);
-                load_row<VPL, false>(rn, p.Rp, t0, d4, lane);
-            }
+            float sc_keep = 0.f;
             const int lim = min(n, base + ADV);
-            for (int k = base; k < lim; ++k) {
+            for (int k = base; k < lim; k += 2) {
                 // keep the ring full: issue the Q[j], X[j] gathers up to edge k + RING_S - 1
                 const int want = min(n, k + RING_S);
                 while (issued < want) {                           // warp-uniform
@@ -258,32 +269,55 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
                     ++cnt_issue;
                     ++issued;
                 }
-                const Row<VPL> sr = sn, r = rn;
-                if (k + 1 < n) {                                  // prefetch the next edge's relation rows (k+1-base <= ADV < 32)
-                    const int t1 = __shfl_sync(FULL, tv, k + 1 - base);
-                    load_row<VPL, false>(sn, p.S, t1, d4, lane);
-                    load_row<VPL, false>(rn, p.Rp, t1, d4, lane);
+                const bool two = k + 1 < lim;                      // warp-uniform
+                // relation rows (L2-resident) of the two edges: plain loads, in flight while we wait on the ring
+                const int t0 = __shfl_sync(FULL, tv, k - base);
+                const int t1 = __shfl_sync(FULL, tv, two ? k + 1 - base : k - base);
+                Row<VPL> s0, r0, s1, r1;
+                load_row<VPL, false>(s0, p.S, t0, d4, lane);
+                load_row<VPL, false>(s1, p.S, t1, d4, lane);
+                load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
+                load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
+                const uint32_t sa = cnt_use % RING_S, sb = (cnt_use + 1) % RING_S;
+                mbar_wait(bars + 8 * sa, (cnt_use / RING_S) & 1);
+                if (two) mbar_wait(bars + 8 * sb, ((cnt_use + 1) / RING_S) & 1);
+                const float* sl0 = slots + (size_t)sa * RING_ROWS * row_f;
+                const float* sl1 = slots + (size_t)(two ? sb : sa) * RING_ROWS * row_f;
+                unsigned b0, b1;
+                float sc0 = ring_logit<VPL>(pi, sl0, s0, av, p.slope, d4, lane, b0);
+                float sc1 = ring_logit<VPL>(pi, sl1, s1, av, p.slope, d4, lane, b1);
+                Row<VPL> x0, x1;
+                lds_row<VPL>(x0, sl0 + row_f, d4, lane);
+                lds_row<VPL>(x1, sl1 + row_f, d4, lane);
+                __syncwarp();                                     // every lane has its copies: the slots may be refilled
+                cnt_use += two ? 2 : 1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sc0 += __shfl_xor_sync(FULL, sc0, o);
+                    sc1 += __shfl_xor_sync(FULL, sc1, o);
                 }
-                const uint32_t s = cnt_use % RING_S;
-                mbar_wait(bars + 8 * s, (cnt_use / RING_S) & 1);
-                ++cnt_use;
-                const float* sl = slots + (size_t)s * RING_ROWS * row_f;
-                Row<VPL> q, x;
-                lds_row<VPL>(q, sl, d4, lane);
-                lds_row<VPL>(x, sl + row_f, d4, lane);
-                __syncwarp();                                     // every lane has its copy: the slot may be refilled
-                const float sc = warp_sum(leaky_dot<VPL>(pi, q, sr, av, p.slope));
-                const float mn = fmaxf(m, sc);
+                if (save) {
+                    store_mask<VPL>(p.mask, item.beg + k, b0, lane);
+                    if (lane == k - base) sc_keep = sc0;
+                    if (two) {
+                        store_mask<VPL>(p.mask, item.beg + k + 1, b1, lane);
+                        if (lane == k + 1 - base) sc_keep = sc1;
+                    }
+                }
+                if (!two) sc1 = -INFINITY;                         // contributes exp(-inf) = 0
+                const float mn = fmaxf(m, fmaxf(sc0, sc1));
                 const float corr = __expf(m - mn);
-                const float pe = __expf(sc - mn);
-                l = l * corr + pe;
+                const float pe0 = __expf(sc0 - mn), pe1 = __expf(sc1 - mn);
+                l = l * corr + pe0 + pe1;
 #pragma unroll
                 for (int i = 0; i < VPL; ++i) {
                     acc.v[i] = corr * acc.v[i];
-                    fma4(acc.v[i], pe, x.v[i] - r.v[i]);
+                    fma4(acc.v[i], pe0, x0.v[i] - r0.v[i]);
+                    fma4(acc.v[i], pe1, x1.v[i] - r1.v[i]);
                 }
                 m = mn;
             }
+            if (save && base + lane < lim) p.logit[item.beg + base + lane] = sc_keep;
         }
         if (item.slot < 0) {
             const float c = p.sqrt_deg[item.seg];
@@ -341,12 +375,12 @@ using namespace jmac;
 
 extern "C" int jmac_edge_fwd(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S, const float* Rp,
                              const float* a_att, float leaky_slope, int d, float* agg, float* lse, void* stream) {
-    return jmac_edge_fwd_fused(plan, P, Q, X, S, Rp, a_att, leaky_slope, d, agg, lse, nullptr, nullptr, stream);
+    return jmac_edge_fwd_fused(plan, P, Q, X, S, Rp, a_att, leaky_slope, d, agg, lse, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float* Q, const float* X, const float* S, const float* Rp,
                                    const float* a_att, float leaky_slope, int d, float* agg, float* lse, const float* Xself, float* T,
-                                   void* stream) {
+                                   void* erec, void* stream) {
     JMAC_ARG(plan && P && Q && X && S && Rp && a_att && agg && lse);
     JMAC_ARG((Xself == nullptr) == (T == nullptr));
     JMAC_ARG(dim_ok(d));
@@ -362,6 +396,8 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     p.d4 = d / 4;
     p.agg = agg; p.lse = lse;
     p.Xself = Xself; p.T = T;
+    p.mask = erec ? erec_mask(erec, plan->E) : nullptr;
+    p.logit = erec ? erec_logit(erec, plan->E, d) : nullptr;
     p.loop_row = Rp + (size_t)(plan->n_rel - 1) * d;     // the self-loop relation is the last row of R'
     p.partial = nullptr;
     if (plan->dst_items.n_slots > 0) {
@@ -373,7 +409,7 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     // The bulk-copy ring variant measures the same as the register-staged kernel on C4 (17.6-18.9 ms vs
     // 18.4 ms: the bound is the memory system's random-1KB-gather rate, not latency hiding -- DESIGN.md
     // section 4), so the simpler kernel stays the default; JMAC_EDGE_RING=1 selects the ring.
-    static const int use_ring = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 0;
+    static const int use_ring = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
     const size_t ring_smem = (size_t)RING_WARPS * RING_S * (RING_ROWS * (size_t)d * 4 + 8);
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL == 1 ? 4 : 2;

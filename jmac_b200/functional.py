@@ -144,18 +144,24 @@ class EdgePhaseFn(torch.autograd.Function):
             if Xself.shape != P.shape:
                 raise ValueError("Xself must be [N_dst, d]")
             T = torch.empty_like(P)
+        # per-edge record (logit + sign mask, later {w, ds}) only when a gradient will be asked for
+        need_grad = any(ctx.needs_input_grad)
+        erec = None
+        if need_grad:
+            erec = torch.empty(max(plan.E, 1) * int(lib.jmac_edge_record_bytes(d)), dtype=torch.uint8, device=X.device)
         with torch.cuda.device(X.device):
             check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
-                                          ptr(Xself), ptr(T), stream_ptr()), "jmac_edge_fwd")
+                                          ptr(Xself), ptr(T), ptr(erec), stream_ptr()), "jmac_edge_fwd")
         ctx.plan, ctx.slope, ctx.fused = plan, float(slope), Xself is not None
-        ctx.save_for_backward(P, Q, X, S, Rp, a, agg, lse)
+        if need_grad:
+            ctx.save_for_backward(P, Q, X, S, Rp, a, agg, lse, erec)
         ctx.a_shape = a_att.shape
         return T if T is not None else agg
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        P, Q, X, S, Rp, a, agg, lse = ctx.saved_tensors
+        P, Q, X, S, Rp, a, agg, lse, erec = ctx.saved_tensors
         plan, slope = ctx.plan, ctx.slope
         d = X.shape[1]
         G = _f32c(g)
@@ -166,14 +172,14 @@ class EdgePhaseFn(torch.autograd.Function):
         dRp = torch.empty_like(Rp)
         dS = torch.empty_like(S)
         da = torch.zeros(d, dtype=torch.float32, device=dev)
-        rec_bytes = int(lib.jmac_edge_record_bytes(d))
-        erec = torch.empty(max(plan.E, 1) * rec_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = stream_ptr()
-            check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G),
-                                        ptr(dP), ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
-            check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(dXe), ptr(dQ), st), "jmac_edge_bwd_src")
-            check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(dRp), ptr(dS), st), "jmac_edge_bwd_rel")
+            check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(X), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
+                                        ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
+            check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
+                  "jmac_edge_bwd_src")
+            check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st),
+                  "jmac_edge_bwd_rel")
         dXself = None
         if ctx.fused:
             dXself = G                                  # T = agg + Xself - Rp[-1]

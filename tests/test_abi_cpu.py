@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_do_not_need_a_gpu():
     from jmac_b200 import _lib
     lib = _lib.load()
-    assert lib.jmac_edge_record_bytes(256) == 40 and lib.jmac_edge_record_bytes(300) == 72 and lib.jmac_edge_record_bytes(7) == 0
+    assert lib.jmac_edge_record_bytes(256) == 44 and lib.jmac_edge_record_bytes(300) == 76 and lib.jmac_edge_record_bytes(7) == 0
     assert lib.jmac_plan_info(None, None) == -1                       # JMAC_EINVAL
     assert b"bad argument" in lib.jmac_last_error()
     assert lib.jmac_plan_destroy(None) == 0

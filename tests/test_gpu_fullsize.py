@@ -109,9 +109,10 @@ def test_c5_alignment_recovers_a_permutation():
     assert int(ranks.max()) == 0 and torch.equal(top1.long(), torch.arange(n, device=dev))
 
 
-def test_ring_variant_of_edge_fwd_matches_oracle():
-    """JMAC_EDGE_RING=1 selects the cp.async.bulk ring kernel (read once per process)."""
-    env = dict(os.environ, JMAC_EDGE_RING="1")
+def test_register_staged_variant_matches_oracle():
+    """JMAC_EDGE_RING=0 selects the register-staged edge kernels instead of the default cp.async.bulk rings
+    (the switch is read once per process)."""
+    env = dict(os.environ, JMAC_EDGE_RING="0")
     out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "smoke:" in out.stdout
