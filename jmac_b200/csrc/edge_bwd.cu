@@ -25,6 +25,7 @@ namespace jmac {
 struct EdgeBwdDstParams {
     const Item* items;
     int n_items;
+    int E;
     const int* csr_src;
     const int* csr_type;
     const float* sqrt_deg;
@@ -305,16 +306,18 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
 constexpr int BWD_RING_S = 12;
 
 struct Ring {
-    float* slots;
-    uint32_t slots_s, bars, row_bytes;
+    uint8_t* slots;
+    uint32_t slots_s, bars, row_bytes, mask_b, slot_bytes;
     int row_f;
     uint32_t cnt_issue, cnt_use;
-    __device__ __forceinline__ void init(uint8_t* raw, int wib, int lane, int d4) {
+    __device__ __forceinline__ void init(uint8_t* raw, int wib, int lane, int d4, int mask_bytes) {
         row_bytes = (uint32_t)d4 * 16;
+        mask_b = (uint32_t)mask_bytes;
+        slot_bytes = row_bytes + mask_b;                       // {gathered row, sign mask of the edge}
         row_f = d4 * 4;
-        slots = reinterpret_cast<float*>(raw) + (size_t)wib * BWD_RING_S * row_f;
+        slots = raw + (size_t)wib * BWD_RING_S * slot_bytes;
         slots_s = smem_addr(slots);
-        bars = smem_addr(raw) + (uint32_t)RING_WARPS * BWD_RING_S * row_bytes + (uint32_t)wib * BWD_RING_S * 8;
+        bars = smem_addr(raw) + (uint32_t)RING_WARPS * BWD_RING_S * slot_bytes + (uint32_t)wib * BWD_RING_S * 8;
         cnt_issue = cnt_use = 0;
         if (lane == 0) {
             for (int s = 0; s < BWD_RING_S; ++s) mbar_init(bars + 8 * s, 1);
@@ -322,22 +325,45 @@ struct Ring {
         }
         __syncwarp();
     }
-    __device__ __forceinline__ void issue(const float* table, int row, int lane) {
+    // one edge: the node row `row` of `table` and the 32/64-byte mask record at CSR position `pos`
+    __device__ __forceinline__ void issue(const float* table, int row, const void* mask, int pos, int lane) {
         if (lane == 0) {
             const uint32_t s = cnt_issue % BWD_RING_S;
-            mbar_expect_tx(bars + 8 * s, row_bytes);
-            bulk_row(slots_s + s * row_bytes, table + (size_t)row * row_f, row_bytes, bars + 8 * s);
+            const uint32_t dst = slots_s + s * slot_bytes;
+            mbar_expect_tx(bars + 8 * s, slot_bytes);
+            bulk_row(dst, table + (size_t)row * row_f, row_bytes, bars + 8 * s);
+            bulk_row(dst + row_bytes, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(mask) + (size_t)pos * mask_b), mask_b, bars + 8 * s);
         }
         ++cnt_issue;
     }
-    // waits for the next slot in consumption order and returns its shared-memory row
-    __device__ __forceinline__ const float* wait_next() {
+    // waits for the next slot in consumption order and returns its shared-memory address
+    __device__ __forceinline__ const uint8_t* wait_next() {
         const uint32_t s = cnt_use % BWD_RING_S;
         mbar_wait(bars + 8 * s, (cnt_use / BWD_RING_S) & 1);
         ++cnt_use;
-        return slots + (size_t)s * row_f;
+        return slots + (size_t)s * slot_bytes;
     }
 };
+
+// Contiguous run of items per warp (see edge_fwd.cu): the index batches and the ring run ahead across segments.
+__device__ __forceinline__ int first_item_at_or_after(const Item* items, int n_items, int pos) {
+    int lo = 0, hi = n_items;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&items[mid].beg) < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// pull the per-segment rows of the NEXT segment towards L2 while the current one is processed (no registers held)
+__device__ __forceinline__ void prefetch_rows_l2(const float* a, const float* b, const float* c, int row, int row_f, int lane) {
+    const int lines = (row_f * 4 + 127) >> 7;                    // 128-byte lines per row (<= 16)
+    const float* t = lane < 8 ? a : (lane < 16 ? b : c);
+    const int ln = lane & 7;
+    if (t != nullptr && lane < 24) {
+        for (int q = ln; q < lines; q += 8)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(t + (size_t)row * row_f + q * 32));
+    }
+}
 
 template <int VPL>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(EdgeBwdDstParams p) {
@@ -348,66 +374,84 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = p.d4;
     Ring ring;
-    ring.init(ring_raw, wib, lane, d4);
+    ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
     Row<VPL> av, da_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     da_acc.zero();
-    const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
     const float hi = 1.f - p.slope;
     constexpr int ADV = (32 - BWD_RING_S) & ~1;
 
-    for (int it = warp; it < p.n_items; it += nwarps) {
-        const Item item = p.items[it];
-        const int n = item.end - item.beg;
-        Row<VPL> gi, mu;
-        load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
-        mu.zero();
-        float gdot = 0.f, ds_sum = 0.f;
-        {
-            Row<VPL> ai;
-            load_row<VPL, true>(ai, p.agg, item.seg, d4, lane);
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) gdot += dot4(gi.v[i], ai.v[i]);
-            gdot = warp_sum(gdot);
+    const int per = (p.E + nwarps - 1) / nwarps;
+    const int it0 = first_item_at_or_after(p.items, p.n_items, min(p.E, warp * per));
+    const int it1 = warp == nwarps - 1 ? p.n_items : first_item_at_or_after(p.items, p.n_items, min(p.E, (warp + 1) * per));
+    if (it0 < it1) {
+        const int stream_end = p.items[it1 - 1].end;
+        Item item = p.items[it0];
+        int batch_base = item.beg, issued = item.beg;             // absolute CSR positions
+        int jv = 0, tv = 0;
+        float sv = 0.f;
+        if (batch_base + lane < stream_end) {
+            jv = __ldg(p.csr_src + batch_base + lane);
+            tv = __ldg(p.csr_type + batch_base + lane);
+            sv = __ldg(p.logit + batch_base + lane);
         }
-        const float lse = p.lse[item.seg];
-        const float c = p.sqrt_deg[item.seg];
-        int issued = 0;
-        for (int base = 0; base < n; base += ADV) {
-            int jv = 0, tv = 0;
-            float sv = 0.f;
-            if (base + lane < n) {
-                jv = __ldg(p.csr_src + item.beg + base + lane);
-                tv = __ldg(p.csr_type + item.beg + base + lane);
-                sv = __ldg(p.logit + item.beg + base + lane);
+        float w_keep = 0.f, ds_keep = 0.f;
+        for (int it = it0; it < it1; ++it) {
+            Item nxt = item;
+            if (it + 1 < it1) {
+                nxt = p.items[it + 1];
+                prefetch_rows_l2(p.G, p.agg, p.P, nxt.seg, d4 * 4, lane);
             }
-            float w_keep = 0.f, ds_keep = 0.f;
-            const int lim = min(n, base + ADV);
-            for (int k = base; k < lim; k += 2) {
-                const int want = min(n, k + BWD_RING_S);
-                while (issued < want) {                              // warp-uniform
-                    ring.issue(p.X, __shfl_sync(FULL, jv, issued - base), lane);
+            Row<VPL> gi, mu;
+            load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
+            mu.zero();
+            float gdot = 0.f, ds_sum = 0.f;
+            {
+                Row<VPL> ai;
+                load_row<VPL, true>(ai, p.agg, item.seg, d4, lane);
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) gdot += dot4(gi.v[i], ai.v[i]);
+                gdot = warp_sum(gdot);
+            }
+            const float lse = p.lse[item.seg];
+            const float c = p.sqrt_deg[item.seg];
+            for (int k = item.beg; k < item.end; k += 2) {
+                if (k - batch_base >= ADV) {                      // next index batch (warp-uniform)
+                    if (batch_base + lane < k) p.ew[batch_base + lane] = make_float2(w_keep, ds_keep);
+                    batch_base = k;
+                    jv = tv = 0;
+                    sv = 0.f;
+                    if (batch_base + lane < stream_end) {
+                        jv = __ldg(p.csr_src + batch_base + lane);
+                        tv = __ldg(p.csr_type + batch_base + lane);
+                        sv = __ldg(p.logit + batch_base + lane);
+                    }
+                }
+                const int want = min(stream_end, k + BWD_RING_S);
+                while (issued < want) {                          // warp-uniform
+                    ring.issue(p.X, __shfl_sync(FULL, jv, issued - batch_base), p.mask, issued, lane);
                     ++issued;
                 }
-                const bool two = k + 1 < lim;
-                const int k1 = two ? k + 1 : k;
-                const int t0 = __shfl_sync(FULL, tv, k - base), t1 = __shfl_sync(FULL, tv, k1 - base);
-                const float sc0 = __shfl_sync(FULL, sv, k - base), sc1 = __shfl_sync(FULL, sv, k1 - base);
+                const bool two = k + 1 < item.end;
+                const int kb = k - batch_base, kb1 = two ? kb + 1 : kb;
+                const int t0 = __shfl_sync(FULL, tv, kb), t1 = __shfl_sync(FULL, tv, kb1);
+                const float sc0 = __shfl_sync(FULL, sv, kb), sc1 = __shfl_sync(FULL, sv, kb1);
                 Row<VPL> r0, r1;
                 load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
                 load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
-                const unsigned b0 = (unsigned)maskp[(size_t)(item.beg + k) * 32 + lane];
-                const unsigned b1 = (unsigned)maskp[(size_t)(item.beg + k1) * 32 + lane];
                 Row<VPL> x0, x1;
-                const float* sl0 = ring.wait_next();
-                lds_row<VPL>(x0, sl0, d4, lane);
+                const uint8_t* sl0 = ring.wait_next();
+                lds_row<VPL>(x0, reinterpret_cast<const float*>(sl0), d4, lane);
+                const unsigned b0 = (unsigned)reinterpret_cast<const mask_t*>(sl0 + ring.row_bytes)[lane];
+                unsigned b1 = b0;
                 if (two) {
-                    const float* sl1 = ring.wait_next();
-                    lds_row<VPL>(x1, sl1, d4, lane);
+                    const uint8_t* sl1 = ring.wait_next();
+                    lds_row<VPL>(x1, reinterpret_cast<const float*>(sl1), d4, lane);
+                    b1 = (unsigned)reinterpret_cast<const mask_t*>(sl1 + ring.row_bytes)[lane];
                 } else {
                     x1 = x0;
                 }
-                __syncwarp();                                        // slots may be refilled
+                __syncwarp();                                    // slots may be refilled
                 float u0 = 0.f, u1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < VPL; ++i) {
@@ -430,24 +474,25 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
                     mu.v[i].z += ((q0 & 4u) ? ds0 : 0.f) + ((q1 & 4u) ? ds1 : 0.f);
                     mu.v[i].w += ((q0 & 8u) ? ds0 : 0.f) + ((q1 & 8u) ? ds1 : 0.f);
                 }
-                if (lane == k - base) { w_keep = c * al0; ds_keep = ds0; }
-                if (two && lane == k + 1 - base) { w_keep = c * al1; ds_keep = ds1; }
+                if (lane == kb) { w_keep = c * al0; ds_keep = ds0; }
+                if (two && lane == kb + 1) { w_keep = c * al1; ds_keep = ds1; }
             }
-            if (base + lane < lim) p.ew[item.beg + base + lane] = make_float2(w_keep, ds_keep);
-        }
-        const float lo = p.slope * ds_sum;
-        Row<VPL> pi;
-        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+            const float lo = p.slope * ds_sum;
+            Row<VPL> pi;
+            load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            mu.v[i].x = fmaf(hi, mu.v[i].x, lo); mu.v[i].y = fmaf(hi, mu.v[i].y, lo);
-            mu.v[i].z = fmaf(hi, mu.v[i].z, lo); mu.v[i].w = fmaf(hi, mu.v[i].w, lo);
-            da_acc.v[i].x = fmaf(pi.v[i].x, mu.v[i].x, da_acc.v[i].x); da_acc.v[i].y = fmaf(pi.v[i].y, mu.v[i].y, da_acc.v[i].y);
-            da_acc.v[i].z = fmaf(pi.v[i].z, mu.v[i].z, da_acc.v[i].z); da_acc.v[i].w = fmaf(pi.v[i].w, mu.v[i].w, da_acc.v[i].w);
-            mu.v[i].x *= av.v[i].x; mu.v[i].y *= av.v[i].y; mu.v[i].z *= av.v[i].z; mu.v[i].w *= av.v[i].w;
+            for (int i = 0; i < VPL; ++i) {
+                mu.v[i].x = fmaf(hi, mu.v[i].x, lo); mu.v[i].y = fmaf(hi, mu.v[i].y, lo);
+                mu.v[i].z = fmaf(hi, mu.v[i].z, lo); mu.v[i].w = fmaf(hi, mu.v[i].w, lo);
+                da_acc.v[i].x = fmaf(pi.v[i].x, mu.v[i].x, da_acc.v[i].x); da_acc.v[i].y = fmaf(pi.v[i].y, mu.v[i].y, da_acc.v[i].y);
+                da_acc.v[i].z = fmaf(pi.v[i].z, mu.v[i].z, da_acc.v[i].z); da_acc.v[i].w = fmaf(pi.v[i].w, mu.v[i].w, da_acc.v[i].w);
+                mu.v[i].x *= av.v[i].x; mu.v[i].y *= av.v[i].y; mu.v[i].z *= av.v[i].z; mu.v[i].w *= av.v[i].w;
+            }
+            if (item.slot < 0) store_row<VPL>(mu, p.dP, item.seg, d4, lane);
+            else store_row<VPL>(mu, p.partial, item.slot, d4, lane);
+            item = nxt;
         }
-        if (item.slot < 0) store_row<VPL>(mu, p.dP, item.seg, d4, lane);
-        else store_row<VPL>(mu, p.partial, item.slot, d4, lane);
+        if (batch_base + lane < stream_end) p.ew[batch_base + lane] = make_float2(w_keep, ds_keep);
     }
     flush_da16<VPL>(da_acc, p.da, d4);
 }
@@ -461,11 +506,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = p.d4;
     Ring ring;
-    ring.init(ring_raw, wib, lane, d4);
+    ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
     Row<VPL> av, da_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     da_acc.zero();
-    const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
     const float sign = MODE == 0 ? 1.f : -1.f;
     constexpr int ADV = (32 - BWD_RING_S) & ~1;
 
@@ -489,23 +533,23 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
             for (int k = base; k < lim; k += 2) {
                 const int want = min(n, k + BWD_RING_S);
                 while (issued < want) {                              // warp-uniform
-                    ring.issue(p.G, __shfl_sync(FULL, iv, issued - base), lane);
+                    ring.issue(p.G, __shfl_sync(FULL, iv, issued - base), p.mask, __shfl_sync(FULL, pv, issued - base), lane);
                     ++issued;
                 }
                 const bool two = k + 1 < lim;
                 const int k1 = two ? k + 1 : k;
-                const int pp0 = __shfl_sync(FULL, pv, k - base), pp1 = __shfl_sync(FULL, pv, k1 - base);
                 const float w0 = __shfl_sync(FULL, e2.x, k - base), d0 = __shfl_sync(FULL, e2.y, k - base);
                 float w1 = __shfl_sync(FULL, e2.x, k1 - base), d1 = __shfl_sync(FULL, e2.y, k1 - base);
                 if (!two) { w1 = 0.f; d1 = 0.f; }
-                const unsigned b0 = (unsigned)maskp[(size_t)pp0 * 32 + lane];
-                const unsigned b1 = (unsigned)maskp[(size_t)pp1 * 32 + lane];
                 Row<VPL> g0, g1;
-                const float* sl0 = ring.wait_next();
-                lds_row<VPL>(g0, sl0, d4, lane);
+                const uint8_t* sl0 = ring.wait_next();
+                lds_row<VPL>(g0, reinterpret_cast<const float*>(sl0), d4, lane);
+                const unsigned b0 = (unsigned)reinterpret_cast<const mask_t*>(sl0 + ring.row_bytes)[lane];
+                unsigned b1 = b0;
                 if (two) {
-                    const float* sl1 = ring.wait_next();
-                    lds_row<VPL>(g1, sl1, d4, lane);
+                    const uint8_t* sl1 = ring.wait_next();
+                    lds_row<VPL>(g1, reinterpret_cast<const float*>(sl1), d4, lane);
+                    b1 = (unsigned)reinterpret_cast<const mask_t*>(sl1 + ring.row_bytes)[lane];
                 } else {
                     g1 = g0;
                 }
@@ -555,10 +599,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
     flush_da16<VPL>(da_acc, p.da, d4);
 }
 
-static inline size_t bwd_ring_smem(int d) { return (size_t)RING_WARPS * BWD_RING_S * ((size_t)d * 4 + 8); }
+static inline size_t bwd_ring_smem(int d) { return (size_t)RING_WARPS * BWD_RING_S * ((size_t)d * 4 + edge_mask_bytes(d) + 8); }
 static inline bool use_ring(int d) {
     static const int on = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
-    return on && bwd_ring_smem(d) <= 220 * 1024;
+    return on && bwd_ring_smem(d) <= 200 * 1024;      // + 16 KB static for the da_att block reduction
 }
 
 }  // namespace jmac
@@ -575,7 +619,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
     JMAC_ARG(dim_ok(d));
     cudaStream_t st = (cudaStream_t)stream;
     EdgeBwdDstParams p;
-    p.items = plan->dst_items.items; p.n_items = plan->dst_items.n_items;
+    p.items = plan->dst_items.items; p.n_items = plan->dst_items.n_items; p.E = (int)plan->E;
     p.csr_src = plan->csr_src; p.csr_type = plan->csr_type; p.sqrt_deg = plan->sqrt_deg;
     p.P = P; p.X = X; p.Rp = Rp; p.a = a_att;
     p.slope = leaky_slope; p.d4 = d / 4;
@@ -593,7 +637,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
     const int threads = 256;
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL <= 2 ? 4 : 2;
-        if (use_ring(d)) {
+        if (use_ring(d) && plan->E > 0) {
             auto kern = edge_bwd_dst_ring_kernel<VPL>;
             JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
             long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;

@@ -20,6 +20,7 @@ namespace jmac {
 struct EdgeFwdParams {
     const Item* items;
     int n_items;
+    int E;
     const int* csr_src;
     const int* csr_type;
     const float* sqrt_deg;
@@ -212,6 +213,19 @@ __device__ __forceinline__ float ring_logit(const Row<VPL>& pi, const float* slo
     return leaky_dot<VPL>(pi, q, sr, av, slope, bits);
 }
 
+// Work decomposition of the ring kernels: every warp owns a CONTIGUOUS run of work items whose edges form one
+// contiguous stream of CSR positions (~E / #warps edges per warp), so the index batches and the gather ring run
+// ahead across segment boundaries -- the per-segment start-up latency of short segments (mean in-degree 3-20
+// on KGs) is paid once per warp instead of once per destination.
+__device__ __forceinline__ int first_item_at_or_after(const Item* items, int n_items, int pos) {
+    int lo = 0, hi = n_items;                      // items are sorted by beg
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&items[mid].beg) < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeFwdParams p) {
     extern __shared__ __align__(16) uint8_t ring_raw[];
@@ -232,92 +246,111 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
     const bool save = p.logit != nullptr;
     Row<VPL> av;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
-    uint32_t cnt_issue = 0, cnt_use = 0;                          // edges issued / consumed by this warp so far
 
-    for (int it = warp; it < p.n_items; it += nwarps) {
-        const Item item = p.items[it];
-        const int n = item.end - item.beg;
-        Row<VPL> pi;
-        load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+    // this warp's run of items: those starting in [warp * per, (warp + 1) * per); the last warp also takes the
+    // trailing empty segments
+    const int per = (p.E + nwarps - 1) / nwarps;
+    const int it0 = first_item_at_or_after(p.items, p.n_items, min(p.E, warp * per));
+    const int it1 = warp == nwarps - 1 ? p.n_items : first_item_at_or_after(p.items, p.n_items, min(p.E, (warp + 1) * per));
+    if (it0 >= it1) return;
+    const int stream_end = p.items[it1 - 1].end;
+    constexpr int ADV = (32 - RING_S) & ~1;
+    uint32_t cnt_issue = 0, cnt_use = 0;                          // edges issued / consumed by this warp so far
+    Item item = p.items[it0];
+    Row<VPL> pi;
+    load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
+    int batch_base = item.beg, issued = item.beg;                 // absolute CSR positions
+    int jv = 0, tv = 0;
+    if (batch_base + lane < stream_end) {
+        jv = __ldg(p.csr_src + batch_base + lane);
+        tv = __ldg(p.csr_type + batch_base + lane);
+    }
+    float sc_keep = 0.f;
+
+    for (int it = it0; it < it1; ++it) {
+        // next segment's descriptor and P row are fetched while this one is processed
+        Item nxt = item;
+        Row<VPL> pn;
+        pn.zero();
+        if (it + 1 < it1) {
+            nxt = p.items[it + 1];
+            load_row<VPL, true>(pn, p.P, nxt.seg, d4, lane);
+        }
         float m = -INFINITY, l = 0.f;
         Row<VPL> acc;
         acc.zero();
-        // indices are fetched 32 at a time but consumed ADV at a time, so that the edge being issued
-        // (up to RING_S - 1 ahead of the one being consumed) is always inside the current batch
-        constexpr int ADV = (32 - RING_S) & ~1;
-        int issued = 0;
-        for (int base = 0; base < n; base += ADV) {
-            int jv = 0, tv = 0;
-            if (base + lane < n) {
-                jv = __ldg(p.csr_src + item.beg + base + lane);
-                tv = __ldg(p.csr_type + item.beg + base + lane);
+        for (int k = item.beg; k < item.end; k += 2) {
+            if (k - batch_base >= ADV) {                          // next index batch (warp-uniform)
+                if (save && batch_base + lane < k) p.logit[batch_base + lane] = sc_keep;
+                batch_base = k;
+                jv = tv = 0;
+                if (batch_base + lane < stream_end) {
+                    jv = __ldg(p.csr_src + batch_base + lane);
+                    tv = __ldg(p.csr_type + batch_base + lane);
+                }
             }
-            float sc_keep = 0.f;
-            const int lim = min(n, base + ADV);
-            for (int k = base; k < lim; k += 2) {
-                // keep the ring full: issue the Q[j], X[j] gathers up to edge k + RING_S - 1
-                const int want = min(n, k + RING_S);
-                while (issued < want) {                           // warp-uniform
-                    const int j = __shfl_sync(FULL, jv, issued - base);
-                    if (lane == 0) {
-                        const uint32_t s = cnt_issue % RING_S;
-                        const uint32_t bar = bars + 8 * s, dst = slots_s + s * RING_ROWS * row_bytes;
-                        mbar_expect_tx(bar, RING_ROWS * row_bytes);
-                        bulk_row(dst, p.Q + (size_t)j * row_f, row_bytes, bar);
-                        bulk_row(dst + row_bytes, p.X + (size_t)j * row_f, row_bytes, bar);
-                    }
-                    ++cnt_issue;
-                    ++issued;
+            // keep the ring full: issue the Q[j], X[j] gathers up to position k + RING_S - 1 (may belong to later segments)
+            const int want = min(stream_end, k + RING_S);
+            while (issued < want) {                               // warp-uniform
+                const int j = __shfl_sync(FULL, jv, issued - batch_base);
+                if (lane == 0) {
+                    const uint32_t s = cnt_issue % RING_S;
+                    const uint32_t bar = bars + 8 * s, dst = slots_s + s * RING_ROWS * row_bytes;
+                    mbar_expect_tx(bar, RING_ROWS * row_bytes);
+                    bulk_row(dst, p.Q + (size_t)j * row_f, row_bytes, bar);
+                    bulk_row(dst + row_bytes, p.X + (size_t)j * row_f, row_bytes, bar);
                 }
-                const bool two = k + 1 < lim;                      // warp-uniform
-                // relation rows (L2-resident) of the two edges: plain loads, in flight while we wait on the ring
-                const int t0 = __shfl_sync(FULL, tv, k - base);
-                const int t1 = __shfl_sync(FULL, tv, two ? k + 1 - base : k - base);
-                Row<VPL> s0, r0, s1, r1;
-                load_row<VPL, false>(s0, p.S, t0, d4, lane);
-                load_row<VPL, false>(s1, p.S, t1, d4, lane);
-                load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
-                load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
-                const uint32_t sa = cnt_use % RING_S, sb = (cnt_use + 1) % RING_S;
-                mbar_wait(bars + 8 * sa, (cnt_use / RING_S) & 1);
-                if (two) mbar_wait(bars + 8 * sb, ((cnt_use + 1) / RING_S) & 1);
-                const float* sl0 = slots + (size_t)sa * RING_ROWS * row_f;
-                const float* sl1 = slots + (size_t)(two ? sb : sa) * RING_ROWS * row_f;
-                unsigned b0, b1;
-                float sc0 = ring_logit<VPL>(pi, sl0, s0, av, p.slope, d4, lane, b0);
-                float sc1 = ring_logit<VPL>(pi, sl1, s1, av, p.slope, d4, lane, b1);
-                Row<VPL> x0, x1;
-                lds_row<VPL>(x0, sl0 + row_f, d4, lane);
-                lds_row<VPL>(x1, sl1 + row_f, d4, lane);
-                __syncwarp();                                     // every lane has its copies: the slots may be refilled
-                cnt_use += two ? 2 : 1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sc0 += __shfl_xor_sync(FULL, sc0, o);
-                    sc1 += __shfl_xor_sync(FULL, sc1, o);
-                }
-                if (save) {
-                    store_mask<VPL>(p.mask, item.beg + k, b0, lane);
-                    if (lane == k - base) sc_keep = sc0;
-                    if (two) {
-                        store_mask<VPL>(p.mask, item.beg + k + 1, b1, lane);
-                        if (lane == k + 1 - base) sc_keep = sc1;
-                    }
-                }
-                if (!two) sc1 = -INFINITY;                         // contributes exp(-inf) = 0
-                const float mn = fmaxf(m, fmaxf(sc0, sc1));
-                const float corr = __expf(m - mn);
-                const float pe0 = __expf(sc0 - mn), pe1 = __expf(sc1 - mn);
-                l = l * corr + pe0 + pe1;
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) {
-                    acc.v[i] = corr * acc.v[i];
-                    fma4(acc.v[i], pe0, x0.v[i] - r0.v[i]);
-                    fma4(acc.v[i], pe1, x1.v[i] - r1.v[i]);
-                }
-                m = mn;
+                ++cnt_issue;
+                ++issued;
             }
-            if (save && base + lane < lim) p.logit[item.beg + base + lane] = sc_keep;
+            const bool two = k + 1 < item.end;                    // warp-uniform
+            const int kb = k - batch_base;
+            // relation rows (L2-resident) of the two edges: plain loads, in flight while we wait on the ring
+            const int t0 = __shfl_sync(FULL, tv, kb);
+            const int t1 = __shfl_sync(FULL, tv, two ? kb + 1 : kb);
+            Row<VPL> s0, r0, s1, r1;
+            load_row<VPL, false>(s0, p.S, t0, d4, lane);
+            load_row<VPL, false>(s1, p.S, t1, d4, lane);
+            load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
+            load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
+            const uint32_t sa = cnt_use % RING_S, sb = (cnt_use + 1) % RING_S;
+            mbar_wait(bars + 8 * sa, (cnt_use / RING_S) & 1);
+            if (two) mbar_wait(bars + 8 * sb, ((cnt_use + 1) / RING_S) & 1);
+            const float* sl0 = slots + (size_t)sa * RING_ROWS * row_f;
+            const float* sl1 = slots + (size_t)(two ? sb : sa) * RING_ROWS * row_f;
+            unsigned b0, b1;
+            float sc0 = ring_logit<VPL>(pi, sl0, s0, av, p.slope, d4, lane, b0);
+            float sc1 = ring_logit<VPL>(pi, sl1, s1, av, p.slope, d4, lane, b1);
+            Row<VPL> x0, x1;
+            lds_row<VPL>(x0, sl0 + row_f, d4, lane);
+            lds_row<VPL>(x1, sl1 + row_f, d4, lane);
+            __syncwarp();                                         // every lane has its copies: the slots may be refilled
+            cnt_use += two ? 2 : 1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sc0 += __shfl_xor_sync(FULL, sc0, o);
+                sc1 += __shfl_xor_sync(FULL, sc1, o);
+            }
+            if (save) {
+                store_mask<VPL>(p.mask, k, b0, lane);
+                if (lane == kb) sc_keep = sc0;
+                if (two) {
+                    store_mask<VPL>(p.mask, k + 1, b1, lane);
+                    if (lane == kb + 1) sc_keep = sc1;
+                }
+            }
+            if (!two) sc1 = -INFINITY;                             // contributes exp(-inf) = 0
+            const float mn = fmaxf(m, fmaxf(sc0, sc1));
+            const float corr = __expf(m - mn);
+            const float pe0 = __expf(sc0 - mn), pe1 = __expf(sc1 - mn);
+            l = l * corr + pe0 + pe1;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                acc.v[i] = corr * acc.v[i];
+                fma4(acc.v[i], pe0, x0.v[i] - r0.v[i]);
+                fma4(acc.v[i], pe1, x1.v[i] - r1.v[i]);
+            }
+            m = mn;
         }
         if (item.slot < 0) {
             const float c = p.sqrt_deg[item.seg];
@@ -332,7 +365,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
             if (lane == 0) *reinterpret_cast<float4*>(ps) = make_float4(m, l, 0.f, 0.f);
             store_row<VPL>(acc, ps + 4, 0, d4, lane);
         }
+        item = nxt;
+        pi = pn;
     }
+    if (save && batch_base + lane < stream_end) p.logit[batch_base + lane] = sc_keep;
 }
 
 // Two-level softmax merge for split (hub) destinations: one warp per split segment.
@@ -388,6 +424,7 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     EdgeFwdParams p;
     p.items = plan->dst_items.items;
     p.n_items = plan->dst_items.n_items;
+    p.E = (int)plan->E;
     p.csr_src = plan->csr_src;
     p.csr_type = plan->csr_type;
     p.sqrt_deg = plan->sqrt_deg;
@@ -413,7 +450,7 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     const size_t ring_smem = (size_t)RING_WARPS * RING_S * (RING_ROWS * (size_t)d * 4 + 8);
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL == 1 ? 4 : 2;
-        if (use_ring && ring_smem <= 220 * 1024) {
+        if (use_ring && plan->E > 0 && ring_smem <= 220 * 1024) {
             // bulk-copy ring variant: one CTA of 12 warps per SM
             auto kern = edge_fwd_ring_kernel<VPL>;
             JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
