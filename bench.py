@@ -383,7 +383,7 @@ def run_b200(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # of this same workload (profiles/ncu_edge_kernels_r01.md); bytes.
-TRAFFIC_NCU = {}      # filled from profiles/ncu_edge_kernels_r01.md once the final kernels are captured
+TRAFFIC_NCU = {"edge_fwd": 91.33e9, "edge_bwd_dst": 52.46e9, "edge_bwd_src": 56.69e9, "edge_bwd_rel": 49.99e9}
 
 
 def main():
