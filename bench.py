@@ -90,6 +90,7 @@ def cpu_layer_step(N, R, E, steps, warmup, seed=0):
     one RelationAwareLayer forward+backward.  Returns (edges/s, seconds per step, threads)."""
     import torch
     from oracle import jmac_oracle as O
+    torch.set_num_threads(len(os.sched_getaffinity(0)))      # all host threads (torchrun exports OMP_NUM_THREADS=1)
     g = torch.Generator().manual_seed(seed)
     ei = torch.randint(0, N, (2, E), generator=g)
     et = torch.randint(0, R, (E,), generator=g)
@@ -369,7 +370,7 @@ def run_b200(args):
         line["e2e"] = {"value": 2.0 * E / (t * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": t,
                        "api": "jmac_b200.RelationAwareLayer.forward/backward x2 from pinned host tensors, graph plan rebuilt each step"}
 
-    if rank == 0 and "cpu" in sections:
+    if single and "cpu" in sections:
         s_ = CPU_SAMPLE
         eps, dt, threads = cpu_layer_step(s_["N"], s_["R"], s_["E"], 2, 1)
         line["cpu_baseline"] = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",

@@ -87,7 +87,7 @@ int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float* Q, const f
                         void* stream);
 
 /* Bytes per edge of the record buffer `erec` shared by forward and the backward passes
- * ({alpha*sqrt(deg), ds_e} 8 B + sign mask 32/64 B + logit 4 B). */
+ * (sign mask 32/64 B + {alpha*sqrt(deg), ds_e} 8 B + logit 4 B).  The buffer must be 32-byte aligned. */
 size_t jmac_edge_record_bytes(int d);
 
 /* Backward of src/jmac_model.py:56-89 + message_passing.py:24-28 in three atomics-free segmented

@@ -205,15 +205,19 @@ inline int persistent_blocks(K kernel, int threads, int n_warp_items) {
 inline bool dim_ok(int d) { return d >= 4 && d <= 512 && (d % 4) == 0; }
 
 // Per-edge record shared by the forward (writes logit + mask) and backward passes, in CSR order:
-//   [0, 8E)            float2 {w_e = alpha_e sqrt(deg_i), ds_e}                 (backward dst pass)
-//   [8E, 8E + MB*E)    sign mask of z_e: lane l of the warp owns MB/32 bytes   (forward)
-//   then               float logit s_e                                          (forward)
+//   [0, MB*E)              sign mask of z_e: lane l of the warp owns MB/32 bytes   (forward)
+//   [MB*E, MB*E + 8E)      float2 {w_e = alpha_e sqrt(deg_i), ds_e}                 (backward dst pass)
+//   then                   float logit s_e                                          (forward)
+// The mask region comes first: its rows are fetched by cp.async.bulk, which needs 16-byte aligned
+// sources for every E (MB is 32 or 64, the buffer itself is at least 32-byte aligned).
 template <int VPL> struct MaskT { typedef uint8_t type; };
 template <> struct MaskT<3> { typedef uint16_t type; };
 template <> struct MaskT<4> { typedef uint16_t type; };
 inline size_t edge_mask_bytes(int d) { return (((d / 4 + 31) / 32) <= 2) ? 32 : 64; }
-inline float2* erec_ew(void* erec) { return reinterpret_cast<float2*>(erec); }
-inline void* erec_mask(void* erec, int64_t E) { return reinterpret_cast<char*>(erec) + sizeof(float2) * (size_t)E; }
+inline void* erec_mask(void* erec, int64_t) { return erec; }
+inline float2* erec_ew(void* erec, int64_t E, int d) {
+    return reinterpret_cast<float2*>(reinterpret_cast<char*>(erec) + edge_mask_bytes(d) * (size_t)E);
+}
 inline float* erec_logit(void* erec, int64_t E, int d) {
     return reinterpret_cast<float*>(reinterpret_cast<char*>(erec) + (sizeof(float2) + edge_mask_bytes(d)) * (size_t)E);
 }

@@ -616,6 +616,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
                                  void* stream) {
     JMAC_ARG(plan && P && X && Rp && a_att && agg && lse && G && dP && da_att);
     JMAC_ARG(plan->E == 0 || erec != nullptr);
+    JMAC_ARG((reinterpret_cast<uintptr_t>(erec) & 31) == 0);
     JMAC_ARG(dim_ok(d));
     cudaStream_t st = (cudaStream_t)stream;
     EdgeBwdDstParams p;
@@ -624,7 +625,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
     p.P = P; p.X = X; p.Rp = Rp; p.a = a_att;
     p.slope = leaky_slope; p.d4 = d / 4;
     p.agg = agg; p.lse = lse; p.G = G; p.dP = dP;
-    p.ew = erec_ew(erec);
+    p.ew = erec_ew(erec, plan->E, d);
     p.mask = erec_mask(erec, plan->E);
     p.logit = erec_logit(erec, plan->E, d);
     p.da = da_att;
@@ -661,6 +662,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
                        float* out_w, float* out_z, float* da_att, cudaStream_t st) {
     JMAC_ARG(plan && G && a_att && Z && out_w && out_z && da_att);
     JMAC_ARG(plan->E == 0 || erec != nullptr);
+    JMAC_ARG((reinterpret_cast<uintptr_t>(erec) & 31) == 0);
     JMAC_ARG(dim_ok(d));
     const ItemList& il = mode == 0 ? plan->src_items : plan->typ_items;
     EdgeBwdGatherParams p;
@@ -668,7 +670,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
     p.pos = mode == 0 ? plan->csc_pos : plan->typ_pos;
     p.dst = mode == 0 ? plan->csc_dst : plan->typ_dst;
     p.G = G;
-    p.ew = erec_ew(const_cast<void*>(erec));
+    p.ew = erec_ew(const_cast<void*>(erec), plan->E, d);
     p.mask = erec_mask(const_cast<void*>(erec), plan->E);
     p.a = a_att; p.Z = Z; p.slope = slope; p.d4 = d / 4;
     p.out_w = out_w; p.out_z = out_z; p.da = da_att;

@@ -422,6 +422,7 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     JMAC_ARG(dim_ok(d));
     cudaStream_t st = (cudaStream_t)stream;
     EdgeFwdParams p;
+    JMAC_ARG((reinterpret_cast<uintptr_t>(erec) & 31) == 0);
     p.items = plan->dst_items.items;
     p.n_items = plan->dst_items.n_items;
     p.E = (int)plan->E;

@@ -134,6 +134,9 @@ def oracle_run(layer, ei, et, x, r, gout, dtype, training=True):
     (700, 5000, 9, 300, 600),         # JMAC_DBPv1 width (3 float4 per lane, ragged tail)
     (400, 3000, 5, 64, 0),            # 1 float4 per lane
     (257, 1000, 3, 128, 300),
+    (3001, 20001, 41, 256, 1501),     # odd E: the record regions behind the masks start at odd multiples of 8 bytes
+    (701, 4999, 9, 300, 333),
+    (33, 1, 2, 256, 0),               # a single edge
     (50, 0, 4, 32, 0),                # E = 0: every node is isolated
 ])
 def test_layer_matches_oracle_fp64_budget(N, E, R, d, hub):
