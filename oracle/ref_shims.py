@@ -72,8 +72,10 @@ def load_train_functions():
     install()
     src = open(os.path.join(REF, "train.py")).read()
     src = src.replace("'--no_name_info, action=", "'--no_name_info', action=")
-    start = src.index("def compute_alignment_quality")
+    start = src.index("def test_alignment_")
     end = src.index("def completion_data_processing")
-    ns = {"torch": torch, "np": np}
-    exec(compile(src[start:end], "train.py[compute_alignment_quality]", "exec"), ns)
+    from modules.finding.evaluation import test
+    from modules.utils.util import get_neg
+    ns = {"torch": torch, "np": np, "test": test, "get_neg": get_neg}
+    exec(compile(src[start:end], "train.py[test_alignment_ .. process_input_data]", "exec"), ns)
     return ns

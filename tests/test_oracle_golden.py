@@ -143,3 +143,34 @@ def test_scatter_restatement_against_naive_loops():
             s = src.numpy()[m]
             e = np.exp(s - s.max(0))
             np.testing.assert_allclose(sm.numpy()[m], e / e.sum(0), atol=1e-12)
+
+
+def test_oracle_on_real_dbp5l_graphs(golden):
+    """The oracle on the el/en graphs of the in-repo DBP-5L data (real hubs, isolated entities) against the
+    reference's trace (oracle/gen_golden_dbp5l.py): seeded init checksums, eval-mode embeddings, the first
+    alignment / completion losses."""
+    from types import SimpleNamespace
+    from jmac_b200.model import JMAC                                   # parameter container only: same init order as the reference
+    g = golden("dbp5l_el_en")
+    K, B = 25, 1000
+    args = SimpleNamespace(dim=256, device="cpu", dropout=0.0, leaky_relu_w=0.05, comp_op="sub", margin_align=1.0, num_negative=K,
+                           margin_completion=5.0, num_gcn_layer=2, no_name_info=True, batch_size=B)
+    ne, nr = int(g["num_entities"]), int(g["num_relations"])
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in JMAC(args, np.zeros((ne, 300), dtype=np.float32), nr, ne).state_dict().items()}
+    for k, v in sd.items():
+        np.testing.assert_allclose([float(v.double().sum()), float(v.double().abs().sum())], g["init." + k], rtol=1e-9, atol=1e-9, err_msg=k)
+    L = lambda k: T(g[k].astype(np.int64))
+    eb1, rb1, eb2, rb2 = (g[k].tolist() for k in ("eb1", "rb1", "eb2", "rb2"))
+    with torch.no_grad():
+        _, ents, _ = O.forward_no_name(sd, L("ei1"), L("et1"), eb1, rb1, training=False)
+        emb = torch.nn.functional.normalize(ents[-1], 2, -1).numpy()
+        np.testing.assert_allclose(emb[::37], g["before.comp1_rows"], atol=1e-5, rtol=1e-4)
+        # train mode (batch statistics), first alignment loss and first completion loss
+        _, e1, _ = O.forward_no_name(sd, L("ei1"), L("et1"), eb1, rb1)
+        _, e2, _ = O.forward_no_name(sd, L("ei2"), L("et2"), eb2, rb2)
+        links = g["links"]
+        fa = {"links": links, "neg_left": np.repeat(links[:, 0], K), "neg_right": g["neg_right"], "neg2_left": g["neg2_left"],
+              "neg2_right": np.repeat(links[:, 1], K), "ent_bases1": eb1, "ent_bases2": eb2, "rel_bases1": rb1, "rel_bases2": rb2}
+        loss = O.alignment_margin_loss(e1[-1], e2[-1], fa, 1.0, K)
+        np.testing.assert_allclose(float(loss), g["align_loss"][0], rtol=1e-4)
