@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 D = 256
 FULL = dict(N=2_000_000, R=2_000, E=40_000_000, B=65_536, K=64, ALIGN=1_048_576)
 CPU_SAMPLE = dict(N=50_000, R=2_000, E=1_000_000)      # same mean degree (20) and width as C4
-ALL_SECTIONS = ("roofline", "scorer", "align", "e2e", "cpu")
+ALL_SECTIONS = ("roofline", "scorer", "linkpred", "align", "e2e", "cpu")
 
 
 def peaks():
@@ -188,6 +188,24 @@ def run_b200(args):
     gen = torch.Generator(device=dev).manual_seed(0)
     ei = torch.randint(0, N, (2, E), device=dev, generator=gen)
     et = torch.randint(0, R, (E,), device=dev, generator=gen)
+    if args.graph == "zipf":
+        # power-law in-degree: destination = rank drawn from Zipf(1.1) over a random permutation of the entities,
+        # capped at 1e5 in-edges per entity (SURVEY 8d, C4 variant).  Inverse-CDF sampling of p(k) ~ k^-1.1, k in [1, N].
+        a = 1.1
+        u = torch.rand(E, device=dev, generator=gen, dtype=torch.float64)
+        k = ((u * (float(N) ** (1 - a) - 1.0) + 1.0) ** (1.0 / (1 - a))).floor().clamp_(1, N).to(torch.int64) - 1
+        cnt = torch.bincount(k, minlength=N)
+        over = cnt > 100_000
+        if bool(over.any()):                               # re-draw the overflow of capped hubs uniformly
+            pos_in_node = torch.argsort(torch.argsort(k, stable=True), stable=True) - (torch.cumsum(cnt, 0) - cnt)[k]
+            redo = over[k] & (pos_in_node >= 100_000)
+            k[redo] = torch.randint(0, N, (int(redo.sum()),), device=dev, generator=gen)
+            del pos_in_node, redo
+        perm = torch.randperm(N, device=dev, generator=gen)
+        ei[0] = perm[k]
+        cfg["workload"] = cfg["workload"].replace("(uniform)", "(Zipf(1.1) in-degree capped at 1e5)")
+        cfg["max_in_degree"] = int(torch.bincount(ei[0], minlength=N).max())
+        del u, k, cnt, over, perm
     x0 = (torch.randn(N, D, device=dev, generator=gen) * 0.1).requires_grad_(True)
     rel = (torch.randn(R, D, device=dev, generator=gen) * 0.1).requires_grad_(True)
     gout = torch.randn(N, D, device=dev, generator=gen)
@@ -316,6 +334,25 @@ def run_b200(args):
                           "note": "includes zero-filling the two dense [N,d] gradient tables per layer (autograd semantics)"}
         del e_tabs, hh, rr, tt
 
+    if single and "linkpred" in sections:
+        # ---- filtered-rank link prediction (src/validate.py:50-70 by counting): Bq queries x N candidates x 2 layers.
+        # Compute-bound on the FP32 pipe: 2 instructions (subtract, |.|-add) per candidate feature; HBM traffic is only
+        # the candidate table per 128-query tile.
+        Bq = 1024
+        rng = np.random.default_rng(1)
+        qe, qr, qt = (torch.from_numpy(rng.integers(0, hi_, Bq)).to(dev) for hi_ in (N, R, N))
+        tabs_e = [x0.detach(), torch.tanh(x0.detach() * 3)]
+        tabs_r = [rel.detach(), rel.detach() * 0.5]
+        t = event_time(lambda: JF.l1_rank(tabs_e, tabs_r, qe, qr, qt), 2, 5)
+        elems = 2.0 * Bq * N * D
+        sm_mhz = line["clocks"].get("sm_mhz") or 1700
+        fp32_peak = 148 * 128 * sm_mhz * 1e6                       # FP32 lane-instructions/s at the clock seen under load
+        line["linkpred"] = {"metric": "linkpred_queries_per_s", "value": Bq / (t * 1e-3), "unit": "queries/s", "ms": t, "queries": Bq,
+                            "candidates": N, "layers": 2, "candidate_distances_per_s": 2.0 * Bq * N / (t * 1e-3) / 2,
+                            "fp32_instr_per_s": 2 * elems / (t * 1e-3), "frac_fp32_pipe": 2 * elems / (t * 1e-3) / fp32_peak,
+                            "bound": "fp32 CUDA cores (2 instr / candidate feature), not HBM"}
+        del tabs_e, tabs_r
+
     if "align" in sections:
         # ---- alignment scorer at scale (C5): bf16 similarity GEMM + CSLS(10) + Hits@k, rows sharded over ranks
         ga = torch.Generator(device=dev).manual_seed(1)
@@ -346,12 +383,23 @@ def run_b200(args):
                          "hits@1": float((ranks < 1).mean()), "hits@10": float((ranks < 10).mean()), "mrr": float((1.0 / (ranks + 1)).mean())}
         del A, Bm
 
-    if single and "e2e" in sections:
-        # ---- e2e: HOST inputs every step (pinned), plan rebuilt, result read back
-        h_x, h_r = x0.detach().cpu().pin_memory(), rel.detach().cpu().pin_memory()
-        h_ei, h_et = ei.cpu().pin_memory(), et.cpu().pin_memory()
+    if "e2e" in sections:
+        # ---- e2e: HOST inputs every step (pinned), graph plan rebuilt, result read back.  N>1: every rank uploads its
+        # own rows of X and its own edge shard (a deployment keeps the partitions on the hosts), the first layer
+        # all-gathers X like every other layer.
+        h_r = rel.detach().cpu().pin_memory()
+        if single:
+            h_x = x0.detach().cpu().pin_memory()
+            h_ei, h_et = ei.cpu().pin_memory(), et.cpu().pin_memory()
+            del ei, et
+            n_loc, n_src, g_loc = N, N, gout
+        else:
+            sh = runner.shard
+            h_x = x0.detach()[sh.lo:sh.hi].cpu().pin_memory()
+            h_ei, h_et = sh.edge_index.cpu().pin_memory(), sh.edge_type.cpu().pin_memory()
+            n_loc, n_src, g_loc = sh.n_loc, sh.n_src, runner._gout_loc
+            runner.plan = None
         h2d = h_x.numel() * 4 + h_r.numel() * 4 + h_ei.numel() * 8 + h_et.numel() * 8
-        del ei, et
         JF.clear_plan_cache()
         torch.cuda.empty_cache()
 
@@ -362,13 +410,43 @@ def run_b200(args):
             dei, det = h_ei.to(dev, non_blocking=True), h_et.to(dev, non_blocking=True)
             for p in params:
                 p.grad = None
-            h = layers[1](layers[0](dx, dr, dei, det), dr, dei, det)
-            loss = (h * gout).sum()
+            if single:
+                h = layers[1](layers[0](dx, dr, dei, det), dr, dei, det)
+            else:
+                runner.plan = JF.GraphPlan(dei, det, n_loc, R + 1, n_src=n_src)
+                h = runner.forward(dx, dr)
+            loss = (h * g_loc).sum()
             loss.backward()
+            if not single:
+                JD.all_reduce_grads(runner.replicated + [dr], dist.group.WORLD)
+                loss = loss.detach().clone()
+                dist.all_reduce(loss)
             return float(loss.item())
-        t = event_time(e2e_step, 1, max(2, min(args.steps, 3)))
-        line["e2e"] = {"value": 2.0 * E / (t * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": t,
-                       "api": "jmac_b200.RelationAwareLayer.forward/backward x2 from pinned host tensors, graph plan rebuilt each step"}
+        try:
+            e2e_step()
+        except Exception as ex:                      # keep the device-timed line even if the host-fed path fails
+            line["e2e_error"] = repr(ex)[:300]
+            if rank == 0:
+                print(json.dumps(line))
+            raise
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(2, min(args.steps, 3))
+        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s3.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e3.record()
+        torch.cuda.synchronize()
+        t = sync_max_ms(s3.elapsed_time(e3)) / n_e2e
+        tot = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot)
+        line["e2e"] = {"value": 2.0 * E / (t * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": 4 * world,
+                       "ms_per_step": t,
+                       "api": "jmac_b200.RelationAwareLayer.forward/backward x2 from pinned host tensors, graph plan rebuilt each step"
+                              + ("" if single else "; every rank uploads its own rows and edge shard (jmac_b200.dist.ShardedEncoder)")}
 
     if single and "cpu" in sections:
         s_ = CPU_SAMPLE
@@ -394,6 +472,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N/E/B for debugging (bench numbers need 1.0)")
+    ap.add_argument("--graph", default="uniform", choices=["uniform", "zipf"], help="C4 in-degree distribution")
     ap.add_argument("--sections", default="all", help="comma list of: " + ",".join(ALL_SECTIONS) + " (or 'all', or '' for headline only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,6 +116,24 @@ def get_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_
     return plan
 
 
+def get_edge_table_plan(edge_index: torch.Tensor, num_ent: int) -> GraphPlan:
+    """Plan for per-edge source tables (comp_op='mult'): destination = edge_index[0], "source" of edge e = row e of an
+    [E,d] table, a single (zero) relation.  Cached like get_plan."""
+    key = ("edge-table", edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_ent), str(edge_index.device))
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return hit[0]
+    dev = edge_index.device
+    E = int(edge_index.shape[1])
+    ei = torch.stack([edge_index[0].to(torch.int64), torch.arange(E, dtype=torch.int64, device=dev)])
+    plan = GraphPlan(ei, torch.zeros(E, dtype=torch.int64, device=dev), num_ent, 1, n_src=max(E, 1))
+    _PLAN_CACHE[key] = (plan, edge_index)
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
 def clear_plan_cache():
     _PLAN_CACHE.clear()
 

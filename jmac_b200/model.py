@@ -68,7 +68,7 @@ class RelationAwareLayer(nn.Module):
 
     def forward(self, ent_emb, rel_emb, edge_index, edge_type):
         if self.comp_op == "mult":
-            raise NotImplementedError("comp_op='mult' does not factor to node level; scheduled (DESIGN.md 'next')")
+            return self.forward_mult(ent_emb, rel_emb, edge_index, edge_type)
         if self.comp_op != "sub":
             raise NotImplementedError                                            # :65-66
         if self.layer_act is not torch.tanh:
@@ -89,6 +89,39 @@ class RelationAwareLayer(nn.Module):
         momentum = self.bn.momentum if self.bn.momentum is not None else 0.1
         return JF.bn_tanh(pre, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var, momentum, self.bn.eps,
                           training, self.dist_group)
+
+
+    def forward_mult(self, ent_emb, rel_emb, edge_index, edge_type):
+        """comp_op='mult' (src/jmac_model.py:63-64): the composed row ``m_e = x_j * r_t`` depends on the edge, so the
+        attention product ``m_e W_bot`` cannot be hoisted to the nodes.  The per-edge table ``M[E,d]`` is materialised
+        once (gather + multiply), its attention projection is ONE E-row product on the tcgen05 3xTF32 kernel, and the
+        edge kernels run unchanged on a bipartite plan whose "sources" are the E rows of M (zero relation tables):
+        logit ``a . lrelu(P[i] + (M W_bot)[e])``, aggregate ``sqrt(deg_i) sum_e alpha_e M[e]``; the message GEMM is still
+        applied once per node after aggregation.  The self loop is ``(x_i * r_loop) W_g``.  Memory is O(E d): meant
+        for the reference's graph sizes (DBP-5L / OpenEA), not for C4."""
+        if self.dist_group is not None:
+            raise NotImplementedError("comp_op='mult' is single-GPU")
+        if self.layer_act is not torch.tanh:
+            raise NotImplementedError("the fused BN+activation kernel implements tanh (BaseModel.act, src/jmac_model.py:118)")
+        num_ent, d = ent_emb.size(0), self.in_channels
+        Rp = self.relation_transform(rel_emb)
+        X = ent_emb.contiguous()
+        ei = JF.as_index(edge_index, X.device)
+        et = JF.as_index(edge_type, X.device)
+        E = ei.shape[1]
+        plan = JF.get_edge_table_plan(edge_index, num_ent)
+        M = X.index_select(0, ei[1]) * Rp.index_select(0, et) if E else X.new_zeros((1, d))
+        P = JF.node_mm(X, self.w_att[:d])
+        Qm = JF.node_mm(M, self.w_att[d:])
+        zero = X.new_zeros((1, d))
+        T = JF.edge_phase(plan, P, Qm, M, zero, zero, self.a_att, self.leaky_slope, X * Rp[-1])
+        pre = JF.node_mm(T, self.gcn_weight * 0.5)
+        training = self.training or not self.bn.track_running_stats
+        if self.training and self.bn.track_running_stats:
+            self.bn.num_batches_tracked += 1
+        momentum = self.bn.momentum if self.bn.momentum is not None else 0.1
+        return JF.bn_tanh(pre, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var, momentum, self.bn.eps,
+                          training, None)
 
 
 class BaseModel(nn.Module):
@@ -233,17 +266,30 @@ class JMAC(BaseModel):
 
     def completion_loss(self, data, edge_index1, edge_type1, edge_index2, edge_type2, feeddict, source=True):
         """:316-380."""
+        return self.completion_loss_multi([data], edge_index1, edge_type1, edge_index2, edge_type2, feeddict, source)[0]
+
+    def completion_loss_multi(self, batches, edge_index1, edge_type1, edge_index2, edge_type2, feeddict, source=True):
+        """Optional multi-batch step: the reference re-encodes both KGs for every 1000-triple batch
+        (:325-326, train.py:332-361); here both encoders run ONCE and every batch of ``batches`` (dicts with
+        batch_h / batch_r / batch_t in the layout of train.py:347-352) is scored against the same embeddings.
+        Returns one loss per batch, each equal to what ``completion_loss`` returns for that batch at the current
+        parameters; ``sum(losses).backward()`` accumulates the gradient of all of them through one encoder backward."""
         links = feeddict["links"]
         _, ents1, rels1 = self.forward_base(edge_index1, edge_type1, feeddict["ent_bases1"], feeddict["rel_bases1"])
         _, ents2, rels2 = self.forward_base(edge_index2, edge_type2, feeddict["ent_bases2"], feeddict["rel_bases2"])
         L = self.args.num_gcn_layer
         ents, rels = (ents1, rels1) if source else (ents2, rels2)
-        per_layer = JF.transe_margin_loss(list(ents[:L]), list(rels[:L]), data["batch_h"], data["batch_r"], data["batch_t"],
-                                          self.args.batch_size, self._margin())
-        loss = per_layer.sum().view(1)      # the reference's loss has shape [1] (margin Parameter broadcast, :374)
+        if getattr(self.args, "normalize_triples", False):   # JMAC_DBPv1/models/jmac_model.py:245-247 scores unit-norm h, r, t
+            ents, rels = [F.normalize(e, 2, -1) for e in ents[:L]], [F.normalize(r, 2, -1) for r in rels[:L]]
+        align = 0
         for layer in range(L):
-            loss = loss + self.alignment_loss_simple(links, ents1[layer], ents2[layer])
-        return loss
+            align = align + self.alignment_loss_simple(links, ents1[layer], ents2[layer])
+        losses = []
+        for data in batches:
+            per_layer = JF.transe_margin_loss(list(ents[:L]), list(rels[:L]), data["batch_h"], data["batch_r"], data["batch_t"],
+                                              self.args.batch_size, self._margin())
+            losses.append(per_layer.sum().view(1) + align)      # shape [1] like the reference (margin Parameter broadcast, :374)
+        return losses
 
     def _margin(self) -> float:
         # margin_completion is a frozen Parameter (:156-157); cache its value to avoid a device sync per step

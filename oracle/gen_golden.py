@@ -152,6 +152,64 @@ def gen_model(seed=11):
     print("model closs", float(res["closs_src"]), float(res["closs_dst"]), "aloss", float(aloss))
 
 
+def gen_model_name(seed=13):
+    """The name-information encoder (JMAC.forward_name, src/jmac_model.py:172-204; dropout off): three
+    RelationAwareLayers, the name projection and the concat-linear fusions, with both losses and all gradients."""
+    from src.jmac_model import JMAC
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    d, B, K = 32, 8, 3
+    n1, n2, nr = 40, 28, 6
+    args = make_args(d, num_negative=K, batch_size=B, no_name_info=False)
+    name_emb = rng.standard_normal((n1 + n2, 300)).astype(np.float32) * 0.3
+    model = JMAC(args, name_emb, 2 * nr, n1 + n2)
+    model.train()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    ei1, et1 = random_graph(rng, n1, 130, nr, hub=2, isolated=(0,))
+    ei2, et2 = random_graph(rng, n2, 90, nr, hub=5, isolated=(1,))
+    links = np.stack([rng.permutation(n1)[:7], rng.permutation(n2)[:7]], 1).astype(np.int64)
+    fd = {"links": links, "ent_bases1": [0, n1], "ent_bases2": [n1, n1 + n2], "rel_bases1": [0, nr], "rel_bases2": [nr, 2 * nr]}
+    t = lambda a: torch.from_numpy(a)
+    sub, rel, obj = rng.integers(0, n1, B), rng.integers(0, nr, B), rng.integers(0, n1, B)
+    neg = rng.integers(0, n1, (B, K))
+    data = {"batch_h": t(np.tile(sub, K + 1)), "batch_r": t(np.tile(rel, K + 1)), "batch_t": t(np.concatenate([obj, neg.reshape(-1)]))}
+    res = {"name_emb": name_emb, "ei1": ei1, "et1": et1, "ei2": ei2, "et2": et2, "links": links, "sub": sub, "rel": rel, "obj": obj,
+           "neg": neg, "n1": n1, "n2": n2, "nr": nr, "B": B, "K": K}
+    for k, v in sd0.items():
+        res["sd." + k] = v
+    out, cembs, crels = model.forward_name(t(ei1), t(et1), [0, n1], [0, nr])
+    res.update({"fwd_out": out, "fwd_comp1": cembs[1], "fwd_rel1": crels[1]})
+    model.zero_grad()
+    closs = model.completion_loss(data, t(ei1), t(et1), t(ei2), t(et2), fd, True)
+    closs.backward()
+    res["closs"] = closs
+    for k, v in model.named_parameters():
+        if v.grad is not None:
+            res["cgrad." + k] = v.grad.clone()
+    model.zero_grad()
+    L = len(links)
+    fa = dict(fd)
+    fa["neg_left"] = (np.ones((L, K)) * links[:, 0].reshape(L, 1)).reshape(-1)
+    fa["neg_right"] = t(rng.integers(0, n2, L * K))
+    fa["neg2_left"] = t(rng.integers(0, n1, L * K))
+    fa["neg2_right"] = (np.ones((L, K)) * links[:, 1].reshape(L, 1)).reshape(-1)
+    aloss = model.alignment_loss(fa, t(ei1), t(et1), t(ei2), t(et2))
+    aloss.backward()
+    res["aloss"] = aloss
+    for k in ("neg_left", "neg_right", "neg2_left", "neg2_right"):
+        res["fa." + k] = fa[k]
+    for k, v in model.named_parameters():
+        if v.grad is not None:
+            res["agrad." + k] = v.grad.clone()
+    model.load_state_dict(sd0)
+    model.eval()
+    with torch.no_grad():
+        emb_a, emb_c = model.get_emb(t(ei1), t(et1), [0, n1], [0, nr])
+    res.update({"emb_align": emb_a, "emb_comp": emb_c})
+    np.savez_compressed(os.path.join(OUT, "model_name.npz"), **npify(res))
+    print("model(name) closs", float(closs), "aloss", float(aloss), "agrads", sum(k.startswith("agrad.") for k in res))
+
+
 def gen_evaluator(seed=5):
     """CompletionEvaluator.test on a small KnowledgeGraph (src/validate.py:22-80)."""
     from src.jmac_model import JMAC
@@ -225,5 +283,6 @@ if __name__ == "__main__":
     gen_layer("train_d256", n=96, e=700, nr=11, d=256, seed=3, training=True)
     gen_layer("mult_d32", n=40, e=160, nr=5, d=32, seed=4, training=True, comp_op="mult")
     gen_model()
+    gen_model_name()
     gen_evaluator()
     gen_alignment()

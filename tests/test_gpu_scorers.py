@@ -223,3 +223,123 @@ def test_completion_evaluator_matches_reference_golden(golden):
             for filt in (1, 0):
                 got = ev.test(args, is_val=bool(is_val), filterr=bool(filt))
                 np.testing.assert_allclose(got, g[f"metrics_val{is_val}_filt{filt}"], rtol=1e-6)
+
+
+def test_dbpv1_flags_normalized_triples_and_relu_relation_transform(golden):
+    """The JMAC_DBPv1 variant's differences on this path are flags of the same kernels: unit-norm h, r, t
+    in the completion scorer (JMAC_DBPv1/models/jmac_model.py:245-250) and ReLU in the relation transform (:27,:51).
+    Checked against the oracle fed the same state dict."""
+    from oracle import jmac_oracle as O
+    g = golden("model_noname")
+    n1, n2, nr, B, K = (int(g[k]) for k in ("n1", "n2", "nr", "B", "K"))
+    model = model_pair(g, make_args(16, num_negative=K, batch_size=B, normalize_triples=True))
+    model.train()
+    fd = {"links": g["links"], "ent_bases1": [0, n1], "ent_bases2": [n1, n1 + n2], "rel_bases1": [0, nr], "rel_bases2": [nr, 2 * nr]}
+    h, r = np.tile(g["sub"], K + 1), np.tile(g["rel"], K + 1)
+    t = np.concatenate([g["obj"], g["neg"].reshape(-1)])
+    data = {"batch_h": T(h).cuda(), "batch_r": T(r).cuda(), "batch_t": T(t).cuda()}
+    loss = model.completion_loss(data, T(g["ei1"]).cuda(), T(g["et1"]).cuda(), T(g["ei2"]).cuda(), T(g["et2"]).cuda(), fd, True)
+    sd = {k[3:]: T(v).double() for k, v in g.items() if k.startswith("sd.")}
+    _, e1, r1 = O.forward_no_name(sd, T(g["ei1"]), T(g["et1"]), [0, n1], [0, nr])
+    _, e2, _ = O.forward_no_name(sd, T(g["ei2"]), T(g["et2"]), [n1, n1 + n2], [nr, 2 * nr])
+    nz = lambda x: torch.nn.functional.normalize(x, 2, -1)
+    want = 0
+    for layer in range(2):
+        l_res, _ = O.transe_margin(nz(e1[layer]), nz(r1[layer]), T(h), T(r), T(t), B, 5.0)
+        want = want + l_res + O.alignment_loss_simple(g["links"], e1[layer], e2[layer])
+    np.testing.assert_allclose(loss.item(), float(want), rtol=1e-4)
+    loss.backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    # ReLU relation transform
+    layer = model.conv1_completion
+    layer.rel_act = "relu"
+    rel = torch.randn(5, 16, device="cuda")
+    got = layer.relation_transform(rel)
+    want = torch.relu(torch.cat([rel, layer.loop_rel]) @ layer.rel_transform_weight1) @ layer.rel_transform_weight2
+    torch.testing.assert_close(got, want)
+
+
+def test_name_encoder_matches_reference_golden(golden):
+    """JMAC.forward_name (src/jmac_model.py:172-204): name projection, three RelationAwareLayers, the concat-linear
+    fusions; forward, both losses and every parameter gradient against the unmodified reference."""
+    from jmac_b200 import JMAC
+    g = golden("model_name")
+    n1, n2, nr, B, K = (int(g[k]) for k in ("n1", "n2", "nr", "B", "K"))
+    args = make_args(32, num_negative=K, batch_size=B, no_name_info=False)
+    model = JMAC(args, g["name_emb"], 2 * nr, n1 + n2).cuda()
+    sd = {k[3:]: T(v) for k, v in g.items() if k.startswith("sd.")}
+    model.load_state_dict(sd)
+    model.train()
+    ei1, et1, ei2, et2 = (T(g[k]).cuda() for k in ("ei1", "et1", "ei2", "et2"))
+    out, cembs, crels = model.forward_name(ei1, et1, [0, n1], [0, nr])
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["fwd_out"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(cembs[1].detach().cpu().numpy(), g["fwd_comp1"], atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(crels[1].detach().cpu().numpy(), g["fwd_rel1"], atol=1e-5, rtol=1e-4)
+    fd = {"links": g["links"], "ent_bases1": [0, n1], "ent_bases2": [n1, n1 + n2], "rel_bases1": [0, nr], "rel_bases2": [nr, 2 * nr]}
+
+    def check_grads(prefix):
+        n = 0
+        for k, v in g.items():
+            if k.startswith(prefix):
+                p = dict(model.named_parameters())[k.split(".", 1)[1]]
+                got = np.zeros_like(v) if p.grad is None else p.grad.cpu().numpy()
+                scale = max(float(np.abs(v).max()), 1e-3)
+                assert float(np.abs(got - v).max()) <= 5e-3 * scale + 2e-5, k
+                n += 1
+        return n
+
+    data = {"batch_h": T(np.tile(g["sub"], K + 1)).cuda(), "batch_r": T(np.tile(g["rel"], K + 1)).cuda(),
+            "batch_t": T(np.concatenate([g["obj"], g["neg"].reshape(-1)])).cuda()}
+    model.zero_grad()
+    closs = model.completion_loss(data, ei1, et1, ei2, et2, fd, True)
+    np.testing.assert_allclose(closs.item(), float(g["closs"].reshape(-1)[0]), rtol=1e-4)
+    closs.backward()
+    assert check_grads("cgrad.") >= 10
+    model.zero_grad()
+    fa = {**fd, "neg_left": g["fa.neg_left"], "neg_right": T(g["fa.neg_right"]), "neg2_left": T(g["fa.neg2_left"]), "neg2_right": g["fa.neg2_right"]}
+    aloss = model.alignment_loss(fa, ei1, et1, ei2, et2)
+    np.testing.assert_allclose(aloss.item(), float(g["aloss"]), rtol=1e-4)
+    aloss.backward()
+    assert check_grads("agrad.") >= 30
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        ea, ec = model.get_emb(ei1, et1, [0, n1], [0, nr])
+    np.testing.assert_allclose(ea, g["emb_align"], atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose(ec, g["emb_comp"], atol=1e-5, rtol=1e-4)
+
+
+def test_completion_loss_multi_equals_separate_calls(golden):
+    """Optional multi-batch step: one encoder pass, several batches -- every loss equals completion_loss on that batch,
+    and the accumulated gradient equals the sum of the separate gradients."""
+    g = golden("model_noname")
+    n1, n2, nr, B, K = (int(g[k]) for k in ("n1", "n2", "nr", "B", "K"))
+    model = model_pair(g, make_args(16, num_negative=K, batch_size=B))
+    model.train()
+    fd = {"links": g["links"], "ent_bases1": [0, n1], "ent_bases2": [n1, n1 + n2], "rel_bases1": [0, nr], "rel_bases2": [nr, 2 * nr]}
+    graphs = [T(g[k]).cuda() for k in ("ei1", "et1", "ei2", "et2")]
+    rng = np.random.default_rng(3)
+    batches = []
+    for _ in range(3):
+        h, r = np.tile(rng.integers(0, n1, B), K + 1), np.tile(rng.integers(0, nr, B), K + 1)
+        batches.append({"batch_h": T(h).cuda(), "batch_r": T(r).cuda(), "batch_t": T(rng.integers(0, n1, (K + 1) * B)).cuda()})
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    want_loss, want_grad = [], None
+    for b in batches:
+        model.load_state_dict(sd0)          # BatchNorm running statistics back to the start
+        model.zero_grad()
+        l = model.completion_loss(b, *graphs, fd, True)
+        l.backward()
+        want_loss.append(l.item())
+        gr = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        want_grad = gr if want_grad is None else {k: want_grad[k] + v for k, v in gr.items()}
+    model.load_state_dict(sd0)
+    model.zero_grad()
+    losses = model.completion_loss_multi(batches, *graphs, fd, True)
+    np.testing.assert_allclose([l.item() for l in losses], want_loss, rtol=1e-6)
+    sum(losses).backward()
+    for k, p in model.named_parameters():
+        if k in want_grad:
+            scale = max(float(want_grad[k].abs().max()), 1e-6)
+            atol = 2e-6 if k.endswith("loop_rel") else 1e-7        # loop_rel: mathematically zero in train mode, rounding noise only
+            assert float((p.grad - want_grad[k]).abs().max()) <= 1e-4 * scale + atol, k
