@@ -309,7 +309,7 @@ struct Ring {
     uint8_t* slots;
     uint32_t slots_s, bars, row_bytes, mask_b, slot_bytes;
     int row_f;
-    uint32_t cnt_issue, cnt_use;
+    uint32_t issue_slot, use_slot, use_phase;                  // maintained incrementally: no modulo by BWD_RING_S in the loops
     __device__ __forceinline__ void init(uint8_t* raw, int wib, int lane, int d4, int mask_bytes) {
         row_bytes = (uint32_t)d4 * 16;
         mask_b = (uint32_t)mask_bytes;
@@ -318,7 +318,7 @@ struct Ring {
         slots = raw + (size_t)wib * BWD_RING_S * slot_bytes;
         slots_s = smem_addr(slots);
         bars = smem_addr(raw) + (uint32_t)RING_WARPS * BWD_RING_S * slot_bytes + (uint32_t)wib * BWD_RING_S * 8;
-        cnt_issue = cnt_use = 0;
+        issue_slot = use_slot = use_phase = 0;
         if (lane == 0) {
             for (int s = 0; s < BWD_RING_S; ++s) mbar_init(bars + 8 * s, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -327,20 +327,20 @@ struct Ring {
     }
     // one edge: the node row `row` of `table` and the 32/64-byte mask record at CSR position `pos`
     __device__ __forceinline__ void issue(const float* table, int row, const void* mask, int pos, int lane) {
+        const uint32_t s = issue_slot;
+        issue_slot = s + 1 == BWD_RING_S ? 0 : s + 1;
         if (lane == 0) {
-            const uint32_t s = cnt_issue % BWD_RING_S;
             const uint32_t dst = slots_s + s * slot_bytes;
             mbar_expect_tx(bars + 8 * s, slot_bytes);
             bulk_row(dst, table + (size_t)row * row_f, row_bytes, bars + 8 * s);
             bulk_row(dst + row_bytes, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(mask) + (size_t)pos * mask_b), mask_b, bars + 8 * s);
         }
-        ++cnt_issue;
     }
     // waits for the next slot in consumption order and returns its shared-memory address
     __device__ __forceinline__ const uint8_t* wait_next() {
-        const uint32_t s = cnt_use % BWD_RING_S;
-        mbar_wait(bars + 8 * s, (cnt_use / BWD_RING_S) & 1);
-        ++cnt_use;
+        const uint32_t s = use_slot;
+        mbar_wait(bars + 8 * s, use_phase);
+        if (s + 1 == BWD_RING_S) { use_slot = 0; use_phase ^= 1; } else use_slot = s + 1;
         return slots + (size_t)s * slot_bytes;
     }
 };
@@ -365,14 +365,14 @@ __device__ __forceinline__ void prefetch_rows_l2(const float* a, const float* b,
     }
 }
 
-template <int VPL>
+template <int VPL, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(EdgeBwdDstParams p) {
     typedef typename MaskT<VPL>::type mask_t;
     extern __shared__ __align__(16) uint8_t ring_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
-    const int d4 = p.d4;
+    const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
     Ring ring;
     ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
     Row<VPL> av, da_acc;
@@ -497,14 +497,14 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
     flush_da16<VPL>(da_acc, p.da, d4);
 }
 
-template <int VPL, int MODE>
+template <int VPL, int MODE, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kernel(EdgeBwdGatherParams p) {
     typedef typename MaskT<VPL>::type mask_t;
     extern __shared__ __align__(16) uint8_t ring_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
-    const int d4 = p.d4;
+    const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
     Ring ring;
     ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
     Row<VPL> av, da_acc;
@@ -639,7 +639,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL <= 2 ? 4 : 2;
         if (use_ring(d) && plan->E > 0) {
-            auto kern = edge_bwd_dst_ring_kernel<VPL>;
+            auto kern = d == VPL * 128 ? edge_bwd_dst_ring_kernel<VPL, true> : edge_bwd_dst_ring_kernel<VPL, false>;
             JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
             long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
             kern<<<(int)(want < sm_count() ? want : sm_count()), RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
@@ -691,7 +691,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
         const int rblocks = (int)(want < sm_count() ? want : sm_count());
         if (mode == 0) {
             if (ring) {
-                auto kern = edge_bwd_gather_ring_kernel<VPL, 0>;
+                auto kern = d == VPL * 128 ? edge_bwd_gather_ring_kernel<VPL, 0, true> : edge_bwd_gather_ring_kernel<VPL, 0, false>;
                 JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
                 kern<<<rblocks, RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
             } else {
@@ -707,7 +707,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
             }
         } else {
             if (ring) {
-                auto kern = edge_bwd_gather_ring_kernel<VPL, 1>;
+                auto kern = d == VPL * 128 ? edge_bwd_gather_ring_kernel<VPL, 1, true> : edge_bwd_gather_ring_kernel<VPL, 1, false>;
                 JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
                 kern<<<rblocks, RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
             } else {

@@ -226,13 +226,15 @@ __device__ __forceinline__ int first_item_at_or_after(const Item* items, int n_i
     return lo;
 }
 
-template <int VPL>
+// FULLROW: d == 128 * VPL, every lane owns VPL complete float4 -- the row loads lose their tail predicates (and the
+// zero-fill moves that go with them), ~10 % fewer instructions per edge in these issue-bound loops.
+template <int VPL, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeFwdParams p) {
     extern __shared__ __align__(16) uint8_t ring_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
-    const int d4 = p.d4;
+    const int d4 = FULLROW ? VPL * 32 : p.d4;
     const uint32_t row_bytes = (uint32_t)d4 * 16;
     const int row_f = d4 * 4;                                   // floats per row
     float* slots = reinterpret_cast<float*>(ring_raw) + (size_t)wib * RING_S * RING_ROWS * row_f;
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
     if (it0 >= it1) return;
     const int stream_end = p.items[it1 - 1].end;
     constexpr int ADV = (32 - RING_S) & ~1;
-    uint32_t cnt_issue = 0, cnt_use = 0;                          // edges issued / consumed by this warp so far
+    uint32_t issue_slot = 0, use_slot = 0, use_phase = 0;         // ring positions, maintained incrementally (no modulo in the loops)
     Item item = p.items[it0];
     Row<VPL> pi;
     load_row<VPL, true>(pi, p.P, item.seg, d4, lane);
@@ -293,14 +295,14 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
             const int want = min(stream_end, k + RING_S);
             while (issued < want) {                               // warp-uniform
                 const int j = __shfl_sync(FULL, jv, issued - batch_base);
+                const uint32_t s = issue_slot;
+                issue_slot = s + 1 == RING_S ? 0 : s + 1;
                 if (lane == 0) {
-                    const uint32_t s = cnt_issue % RING_S;
                     const uint32_t bar = bars + 8 * s, dst = slots_s + s * RING_ROWS * row_bytes;
                     mbar_expect_tx(bar, RING_ROWS * row_bytes);
                     bulk_row(dst, p.Q + (size_t)j * row_f, row_bytes, bar);
                     bulk_row(dst + row_bytes, p.X + (size_t)j * row_f, row_bytes, bar);
                 }
-                ++cnt_issue;
                 ++issued;
             }
             const bool two = k + 1 < item.end;                    // warp-uniform
@@ -313,9 +315,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
             load_row<VPL, false>(s1, p.S, t1, d4, lane);
             load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
             load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
-            const uint32_t sa = cnt_use % RING_S, sb = (cnt_use + 1) % RING_S;
-            mbar_wait(bars + 8 * sa, (cnt_use / RING_S) & 1);
-            if (two) mbar_wait(bars + 8 * sb, ((cnt_use + 1) / RING_S) & 1);
+            const uint32_t sa = use_slot, sb = sa + 1 == RING_S ? 0 : sa + 1;
+            const uint32_t pb = sa + 1 == RING_S ? use_phase ^ 1 : use_phase;
+            mbar_wait(bars + 8 * sa, use_phase);
+            if (two) mbar_wait(bars + 8 * sb, pb);
             const float* sl0 = slots + (size_t)sa * RING_ROWS * row_f;
             const float* sl1 = slots + (size_t)(two ? sb : sa) * RING_ROWS * row_f;
             unsigned b0, b1;
@@ -325,7 +328,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
             lds_row<VPL>(x0, sl0 + row_f, d4, lane);
             lds_row<VPL>(x1, sl1 + row_f, d4, lane);
             __syncwarp();                                         // every lane has its copies: the slots may be refilled
-            cnt_use += two ? 2 : 1;
+            if (two) { use_slot = sb + 1 == RING_S ? 0 : sb + 1; use_phase = sb + 1 == RING_S ? pb ^ 1 : pb; }
+            else { use_slot = sb; use_phase = pb; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 sc0 += __shfl_xor_sync(FULL, sc0, o);
@@ -453,7 +457,7 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
         constexpr int U = VPL == 1 ? 4 : 2;
         if (use_ring && plan->E > 0 && ring_smem <= 220 * 1024) {
             // bulk-copy ring variant: one CTA of 12 warps per SM
-            auto kern = edge_fwd_ring_kernel<VPL>;
+            auto kern = d == VPL * 128 ? edge_fwd_ring_kernel<VPL, true> : edge_fwd_ring_kernel<VPL, false>;
             JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
             long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
             int blocks = (int)(want < sm_count() ? want : sm_count());
