@@ -336,6 +336,22 @@ struct Ring {
             bulk_row(dst + row_bytes, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(mask) + (size_t)pos * mask_b), mask_b, bars + 8 * s);
         }
     }
+    // two edges under one elected-lane region (steady state of the pair loops)
+    __device__ __forceinline__ void issue2(const float* table, int row0, int row1, const void* mask, int pos0, int pos1, int lane) {
+        const uint32_t s0 = issue_slot;
+        const uint32_t s1 = s0 + 1 == BWD_RING_S ? 0 : s0 + 1;
+        issue_slot = s1 + 1 == BWD_RING_S ? 0 : s1 + 1;
+        if (lane == 0) {
+            const uint32_t d0 = slots_s + s0 * slot_bytes, d1 = slots_s + s1 * slot_bytes;
+            const uint8_t* mb = reinterpret_cast<const uint8_t*>(mask);
+            mbar_expect_tx(bars + 8 * s0, slot_bytes);
+            bulk_row(d0, table + (size_t)row0 * row_f, row_bytes, bars + 8 * s0);
+            bulk_row(d0 + row_bytes, reinterpret_cast<const float*>(mb + (size_t)pos0 * mask_b), mask_b, bars + 8 * s0);
+            mbar_expect_tx(bars + 8 * s1, slot_bytes);
+            bulk_row(d1, table + (size_t)row1 * row_f, row_bytes, bars + 8 * s1);
+            bulk_row(d1 + row_bytes, reinterpret_cast<const float*>(mb + (size_t)pos1 * mask_b), mask_b, bars + 8 * s1);
+        }
+    }
     // waits for the next slot in consumption order and returns its shared-memory address
     __device__ __forceinline__ const uint8_t* wait_next() {
         const uint32_t s = use_slot;
@@ -428,7 +444,12 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
                     }
                 }
                 const int want = min(stream_end, k + BWD_RING_S);
-                while (issued < want) {                          // warp-uniform
+                while (issued + 1 < want) {                      // warp-uniform; steady state: one pair per iteration
+                    ring.issue2(p.X, __shfl_sync(FULL, jv, issued - batch_base), __shfl_sync(FULL, jv, issued + 1 - batch_base), p.mask, issued,
+                                issued + 1, lane);
+                    issued += 2;
+                }
+                if (issued < want) {
                     ring.issue(p.X, __shfl_sync(FULL, jv, issued - batch_base), p.mask, issued, lane);
                     ++issued;
                 }
@@ -532,7 +553,12 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
             const int lim = min(n, base + ADV);
             for (int k = base; k < lim; k += 2) {
                 const int want = min(n, k + BWD_RING_S);
-                while (issued < want) {                              // warp-uniform
+                while (issued + 1 < want) {                          // warp-uniform; steady state: one pair per iteration
+                    ring.issue2(p.G, __shfl_sync(FULL, iv, issued - base), __shfl_sync(FULL, iv, issued + 1 - base), p.mask,
+                                __shfl_sync(FULL, pv, issued - base), __shfl_sync(FULL, pv, issued + 1 - base), lane);
+                    issued += 2;
+                }
+                if (issued < want) {
                     ring.issue(p.G, __shfl_sync(FULL, iv, issued - base), p.mask, __shfl_sync(FULL, pv, issued - base), lane);
                     ++issued;
                 }

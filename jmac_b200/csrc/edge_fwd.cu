@@ -50,21 +50,36 @@ __device__ __forceinline__ void store_self_fused(const EdgeFwdParams& p, const R
     store_row<VPL>(xs, p.T, seg, d4, lane);
 }
 
+// a . lrelu(z) for z = P[i] + Q[j] - S[t], and the sign mask of z (bit 4*i + c <=> component c of float4 #i is > 0).
+// Works on nz = S - (P + Q) = -z (exact): the IEEE sign bit of nz is set exactly when z > 0 (z == 0 gives +0, "not
+// positive", the reference's `z > 0` test), so the mask is built by shifting one sign bit per feature into a
+// register (one funnel shift each), and -lrelu(z) = min(nz, slope * nz) for slope <= 1 (max otherwise) is one
+// multiply + one min/max: 6 instructions per feature instead of 8, same rounding as the select form.
 template <int VPL>
 __device__ __forceinline__ float leaky_dot(const Row<VPL>& pi, const Row<VPL>& q, const Row<VPL>& s, const Row<VPL>& a, float slope,
                                            unsigned& bits) {
     float part = 0.f;
-    bits = 0u;
+    unsigned b = 0u;
+    const bool use_min = slope <= 1.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        float4 z = pi.v[i] + q.v[i] - s.v[i];
-        bits |= ((z.x > 0.f ? 1u : 0u) | (z.y > 0.f ? 2u : 0u) | (z.z > 0.f ? 4u : 0u) | (z.w > 0.f ? 8u : 0u)) << (4 * i);
-        z.x = z.x > 0.f ? z.x : slope * z.x;
-        z.y = z.y > 0.f ? z.y : slope * z.y;
-        z.z = z.z > 0.f ? z.z : slope * z.z;
-        z.w = z.w > 0.f ? z.w : slope * z.w;
-        part += dot4(a.v[i], z);
+    for (int i = VPL - 1; i >= 0; --i) {
+        const float4 nz = s.v[i] - (pi.v[i] + q.v[i]);
+        b = __funnelshift_l(__float_as_uint(nz.w), b, 1);
+        b = __funnelshift_l(__float_as_uint(nz.z), b, 1);
+        b = __funnelshift_l(__float_as_uint(nz.y), b, 1);
+        b = __funnelshift_l(__float_as_uint(nz.x), b, 1);
+        float4 m;
+        m.x = use_min ? fminf(nz.x, slope * nz.x) : fmaxf(nz.x, slope * nz.x);
+        m.y = use_min ? fminf(nz.y, slope * nz.y) : fmaxf(nz.y, slope * nz.y);
+        m.z = use_min ? fminf(nz.z, slope * nz.z) : fmaxf(nz.z, slope * nz.z);
+        m.w = use_min ? fminf(nz.w, slope * nz.w) : fmaxf(nz.w, slope * nz.w);
+        float pp = -a.v[i].x * m.x;                     // one short chain per float4, summed at the end
+        pp = fmaf(-a.v[i].y, m.y, pp);
+        pp = fmaf(-a.v[i].z, m.z, pp);
+        pp = fmaf(-a.v[i].w, m.w, pp);
+        part += pp;
     }
+    bits = b;
     return part;
 }
 
@@ -293,7 +308,23 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
             }
             // keep the ring full: issue the Q[j], X[j] gathers up to position k + RING_S - 1 (may belong to later segments)
             const int want = min(stream_end, k + RING_S);
-            while (issued < want) {                               // warp-uniform
+            while (issued + 1 < want) {                           // warp-uniform; steady state: one pair per iteration
+                const int j0 = __shfl_sync(FULL, jv, issued - batch_base), j1 = __shfl_sync(FULL, jv, issued + 1 - batch_base);
+                const uint32_t s0 = issue_slot, s1 = s0 + 1 == RING_S ? 0 : s0 + 1;
+                issue_slot = s1 + 1 == RING_S ? 0 : s1 + 1;
+                if (lane == 0) {
+                    const uint32_t bar0 = bars + 8 * s0, dst0 = slots_s + s0 * RING_ROWS * row_bytes;
+                    const uint32_t bar1 = bars + 8 * s1, dst1 = slots_s + s1 * RING_ROWS * row_bytes;
+                    mbar_expect_tx(bar0, RING_ROWS * row_bytes);
+                    bulk_row(dst0, p.Q + (size_t)j0 * row_f, row_bytes, bar0);
+                    bulk_row(dst0 + row_bytes, p.X + (size_t)j0 * row_f, row_bytes, bar0);
+                    mbar_expect_tx(bar1, RING_ROWS * row_bytes);
+                    bulk_row(dst1, p.Q + (size_t)j1 * row_f, row_bytes, bar1);
+                    bulk_row(dst1 + row_bytes, p.X + (size_t)j1 * row_f, row_bytes, bar1);
+                }
+                issued += 2;
+            }
+            if (issued < want) {
                 const int j = __shfl_sync(FULL, jv, issued - batch_base);
                 const uint32_t s = issue_slot;
                 issue_slot = s + 1 == RING_S ? 0 : s + 1;
