@@ -28,9 +28,10 @@ namespace jmac {
 constexpr int SIM_BM = 256, SIM_BN = 128, SIM_BK = 64, SIM_NS = 6;
 constexpr int SIM_A_SLICE = SIM_BM * SIM_BK * 2;   // 32 KB
 constexpr int SIM_B_SLICE = SIM_BN * SIM_BK * 2;   // 16 KB
-constexpr int SIM_MAX_KS = 4;                       // K <= 256
+constexpr int SIM_MAX_KS = 5;                       // K <= 320 (JMAC_DBPv1's d = 300); the A block stays resident
+constexpr int SIM_BASE_KS = 4;                      // up to K = 256 the B ring has SIM_NS slots, beyond it two fewer (same total)
 constexpr int SIM_THREADS = 320;
-constexpr int SIM_SMEM = SIM_MAX_KS * SIM_A_SLICE + SIM_NS * SIM_B_SLICE + 1024 /*align*/ + 256 /*barriers*/ + 2 * SIM_BN * 4 /*r2 ring*/;
+constexpr int SIM_SMEM = SIM_BASE_KS * SIM_A_SLICE + SIM_NS * SIM_B_SLICE + 1024 /*align*/ + 256 /*barriers*/ + 2 * SIM_BN * 4 /*r2 ring*/;
 static_assert(SIM_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct SimParams {
@@ -129,8 +130,11 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
     const uint32_t smem_a = base;
-    const uint32_t smem_b = base + SIM_MAX_KS * SIM_A_SLICE;
-    const uint32_t bars = smem_b + SIM_NS * SIM_B_SLICE;
+    // K <= 256: 4 resident A slices + a 6-slot B ring; K = 320: 5 A slices + 4 B slots (one A slice = two B slices)
+    const uint32_t a_slices = p.nks > SIM_BASE_KS ? (uint32_t)p.nks : (uint32_t)SIM_BASE_KS;
+    const uint32_t ns = SIM_NS - 2 * (a_slices - SIM_BASE_KS);
+    const uint32_t smem_b = base + a_slices * SIM_A_SLICE;
+    const uint32_t bars = smem_b + ns * SIM_B_SLICE;
     // barrier map (8 B each)
     const uint32_t full0 = bars, empty0 = bars + 8 * SIM_NS, a_full = bars + 16 * SIM_NS, a_empty = a_full + 8;
     const uint32_t t_full0 = a_empty + 8, t_empty0 = t_full0 + 16, tmem_slot = t_empty0 + 16;
@@ -160,14 +164,14 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it = 0, rcount = 0, tcount = 0;
+            uint32_t it = 0, itp = 0, rcount = 0, tcount = 0;      // it: B ring slot, itp: its phase
             for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++rcount) {
                 mbar_wait(a_empty, (rcount & 1) ^ 1);
                 mbar_expect_tx(a_full, (uint32_t)p.nks * SIM_A_SLICE);
                 for (int ks = 0; ks < p.nks; ++ks) tma_load_2d(smem_a + ks * SIM_A_SLICE, &map_a, a_full, ks * SIM_BK, rb * SIM_BM);
                 for (int ct = 0; ct < n_ct; ++ct, ++tcount) {
-                    for (int ks = 0; ks < p.nks; ++ks, ++it) {
-                        const uint32_t slot = it % SIM_NS, ph = (it / SIM_NS) & 1;
+                    for (int ks = 0; ks < p.nks; ++ks, it = it + 1 == ns ? 0 : it + 1, itp ^= (it == 0)) {
+                        const uint32_t slot = it, ph = itp;
                         mbar_wait(empty0 + 8 * slot, ph ^ 1);
                         mbar_expect_tx(full0 + 8 * slot, SIM_B_SLICE);
                         tma_load_2d(smem_b + slot * SIM_B_SLICE, &map_b, full0 + 8 * slot, ks * SIM_BK, ct * SIM_BN);
@@ -188,7 +192,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             // kind::f16, A=B=BF16, D=F32, both K-major, M=128, N=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SIM_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t it = 0, tcount = 0, rcount = 0;
+            uint32_t it = 0, itp = 0, tcount = 0, rcount = 0;
             for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++rcount) {
                 mbar_wait(a_full, rcount & 1);
                 tc_fence_after();
@@ -196,8 +200,8 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                     mbar_wait(t_empty0 + 8 * acc, aph ^ 1);
                     tc_fence_after();
-                    for (int ks = 0; ks < p.nks; ++ks, ++it) {
-                        const uint32_t slot = it % SIM_NS, ph = (it / SIM_NS) & 1;
+                    for (int ks = 0; ks < p.nks; ++ks, it = it + 1 == ns ? 0 : it + 1, itp ^= (it == 0)) {
+                        const uint32_t slot = it, ph = itp;
                         mbar_wait(full0 + 8 * slot, ph);
                         tc_fence_after();
                         const uint64_t bdesc = umma_desc(smem_b + slot * SIM_B_SLICE);

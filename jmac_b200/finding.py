@@ -38,8 +38,8 @@ def to_bf16_rows(x: torch.Tensor, idx=None, normalize=False) -> torch.Tensor:
     lib = _lib.load()
     n_src, d = x.shape
     dpad = (d + 63) // 64 * 64
-    if dpad > 256:
-        raise NotImplementedError("similarity GEMM keeps the A block resident: d <= 256 in this version")
+    if dpad > 320:
+        raise NotImplementedError("similarity GEMM keeps the A block resident: d <= 320 in this version")
     if idx is not None:
         idx = as_index(idx, x.device).reshape(-1)
     n = int(idx.numel()) if idx is not None else n_src

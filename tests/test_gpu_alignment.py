@@ -29,7 +29,8 @@ def planted(n1, n2, d, seed, noise=1.0):
     return unit(e1).astype(np.float32), unit(e2).astype(np.float32)
 
 
-@pytest.mark.parametrize("n1,n2,d,k", [(300, 500, 64, 10), (1000, 777, 256, 10), (257, 129, 100, 5), (513, 2000, 256, 25), (64, 64, 32, 1)])
+@pytest.mark.parametrize("n1,n2,d,k", [(300, 500, 64, 10), (1000, 777, 256, 10), (257, 129, 100, 5), (513, 2000, 256, 25), (64, 64, 32, 1),
+                                         (700, 1500, 300, 25)])
 def test_sim_topk_matches_numpy_on_bf16_inputs(n1, n2, d, k):
     from jmac_b200 import finding as F
     e1, e2 = planted(n1, n2, d, n1 + n2)
@@ -52,7 +53,9 @@ def test_sim_topk_matches_numpy_on_bf16_inputs(n1, n2, d, k):
     assert np.array_equal(topi[clear], ref_i[clear])                   # bit-exact indices away from documented ties
 
 
-@pytest.mark.parametrize("n,d,csls,metric", [(700, 256, 10, "cosine"), (515, 64, 5, "inner"), (300, 128, 0, "cosine"), (1000, 256, 0, "inner")])
+@pytest.mark.parametrize("n,d,csls,metric", [(700, 256, 10, "cosine"), (515, 64, 5, "inner"), (300, 128, 0, "cosine"), (1000, 256, 0, "inner"),
+                                              (4500, 256, 10, "cosine"),       # C3: the OpenEA-shape seed set (30 % of 15k)
+                                              (900, 300, 10, "cosine"), (600, 300, 0, "inner")])   # JMAC_DBPv1 width: 5 resident K slices, 4-slot B ring
 def test_alignment_ranks_match_oracle_on_bf16_inputs(n, d, csls, metric):
     from jmac_b200 import finding as F
     e1, e2 = planted(n, n, d, n * 3 + csls, noise=1.5)
