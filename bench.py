@@ -332,6 +332,20 @@ def run_b200(args):
         line["scorer"] = {"metric": "triples_scored_per_s_fwd_bwd", "value": scored / (t * 1e-3), "unit": "triples/s", "ms": t,
                           "batch": B, "negatives": K, "layers": 2, "algo_GBps": sbytes / t / 1e6, "frac_hbm": sbytes / t / 1e6 / hbm_peak,
                           "note": "includes zero-filling the two dense [N,d] gradient tables per layer (autograd semantics)"}
+        # the reference's default batch (train.py:64, 1000 positives): latency- and zero-fill-bound, reported as is
+        B1 = 1000
+        hh1 = torch.from_numpy(np.tile(rng.integers(0, N, B1), K + 1)).to(dev)
+        rr1 = torch.from_numpy(np.tile(rng.integers(0, R, B1), K + 1)).to(dev)
+        tt1 = torch.from_numpy(rng.integers(0, N, (K + 1) * B1)).to(dev)
+
+        def scorer_step_small():
+            for t_ in e_tabs + r_tabs:
+                t_.grad = None
+            JF.transe_margin_loss(e_tabs, r_tabs, hh1, rr1, tt1, B1, 5.0).sum().backward()
+        t1 = event_time(scorer_step_small, 3, 10)
+        line["scorer"]["batch_1000"] = {"value": (K + 1) * B1 / (t1 * 1e-3), "unit": "triples/s", "ms": t1,
+                                        "note": "4 GB of gradient-table zero fill per step dominates at this batch size"}
+        del hh1, rr1, tt1
         del e_tabs, hh, rr, tt
 
     if single and "linkpred" in sections:
