@@ -52,11 +52,26 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.all_rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
+
+    @property
+    def rows(self):
+        """samples that arrived inside the timed region (the sampler itself is started earlier: nvidia-smi needs ~0.5 s to come up)"""
+        if self.t0 is None:
+            return [r for _, r in self.all_rows]
+        t1 = self.t1 if self.t1 is not None else time.monotonic()
+        return [r for t, r in self.all_rows if self.t0 <= t <= t1 + 0.05]
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -66,7 +81,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.all_rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -229,20 +244,22 @@ def run_b200(args):
             h.backward(gout)
 
     # ---- headline: W warm-up, exactly K timed steps, barrier + sync on both sides, max over ranks
-    for _ in range(args.warmup):
-        step_fn()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    n0 = lib.jmac_launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:                       # started before the warm-up, only samples inside the timed region count
+        for _ in range(args.warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n0 = lib.jmac_launch_count()
         torch.cuda.nvtx.range_push("timed")
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk.mark_start()
         s.record()
         for _ in range(args.steps):
             step_fn()
         e.record()
         torch.cuda.synchronize()
+        clk.mark_end()
         torch.cuda.nvtx.range_pop()
     launches = int(lib.jmac_launch_count() - n0)
     total_ms = sync_max_ms(s.elapsed_time(e))
@@ -312,9 +329,10 @@ def run_b200(args):
                             "kernels": kernels}
         del agg, lse, Tbuf, dP, dXe, dQ, erec, P, Q
 
-    if single and "scorer" in sections:
-        # ---- completion scorer, fwd+bwd, reference batch layout
-        rng = np.random.default_rng(0)
+    if "scorer" in sections:
+        # ---- completion scorer, fwd+bwd, reference batch layout.  N>1: independent triples -- every rank scores its own batch of
+        # B positives against its replica of the tables, no collective in the data path (weak scaling)
+        rng = np.random.default_rng(rank)
         hh = torch.from_numpy(np.tile(rng.integers(0, N, B), K + 1)).to(dev)
         rr = torch.from_numpy(np.tile(rng.integers(0, R, B), K + 1)).to(dev)
         tt = torch.from_numpy(rng.integers(0, N, (K + 1) * B)).to(dev)
@@ -326,11 +344,12 @@ def run_b200(args):
                 t_.grad = None
             loss = JF.transe_margin_loss(e_tabs, r_tabs, hh, rr, tt, B, 5.0)
             loss.sum().backward()
-        t = event_time(scorer_step, 3, 10)
-        scored = (K + 1) * B
+        t = sync_max_ms(event_time(scorer_step, 3, 10))
+        scored = (K + 1) * B * world
         sbytes = 2 * 3 * (K + 3) * B * D * 4
         line["scorer"] = {"metric": "triples_scored_per_s_fwd_bwd", "value": scored / (t * 1e-3), "unit": "triples/s", "ms": t,
-                          "batch": B, "negatives": K, "layers": 2, "algo_GBps": sbytes / t / 1e6, "frac_hbm": sbytes / t / 1e6 / hbm_peak,
+                          "batch": B, "batch_per_gpu": B, "scaling": "weak", "negatives": K, "layers": 2, "algo_GBps": sbytes / t / 1e6,
+                          "frac_hbm": sbytes / t / 1e6 / hbm_peak,
                           "note": "includes zero-filling the two dense [N,d] gradient tables per layer (autograd semantics)"}
         # the reference's default batch (train.py:64, 1000 positives): latency- and zero-fill-bound, reported as is
         B1 = 1000
@@ -342,27 +361,28 @@ def run_b200(args):
             for t_ in e_tabs + r_tabs:
                 t_.grad = None
             JF.transe_margin_loss(e_tabs, r_tabs, hh1, rr1, tt1, B1, 5.0).sum().backward()
-        t1 = event_time(scorer_step_small, 3, 10)
-        line["scorer"]["batch_1000"] = {"value": (K + 1) * B1 / (t1 * 1e-3), "unit": "triples/s", "ms": t1,
+        t1 = sync_max_ms(event_time(scorer_step_small, 3, 10))
+        line["scorer"]["batch_1000"] = {"value": (K + 1) * B1 * world / (t1 * 1e-3), "unit": "triples/s", "ms": t1,
                                         "note": "4 GB of gradient-table zero fill per step dominates at this batch size"}
         del hh1, rr1, tt1
         del e_tabs, hh, rr, tt
 
-    if single and "linkpred" in sections:
+    if "linkpred" in sections:
         # ---- filtered-rank link prediction (src/validate.py:50-70 by counting): Bq queries x N candidates x 2 layers.
         # Compute-bound on the FP32 pipe: 2 instructions (subtract, |.|-add) per candidate feature; HBM traffic is only
         # the candidate table per 128-query tile.
-        Bq = 1024
-        rng = np.random.default_rng(1)
+        Bq = 1024                                                  # per GPU: queries are independent (weak scaling, no collective)
+        rng = np.random.default_rng(100 + rank)
         qe, qr, qt = (torch.from_numpy(rng.integers(0, hi_, Bq)).to(dev) for hi_ in (N, R, N))
         tabs_e = [x0.detach(), torch.tanh(x0.detach() * 3)]
         tabs_r = [rel.detach(), rel.detach() * 0.5]
-        t = event_time(lambda: JF.l1_rank(tabs_e, tabs_r, qe, qr, qt), 2, 5)
+        t = sync_max_ms(event_time(lambda: JF.l1_rank(tabs_e, tabs_r, qe, qr, qt), 2, 5))
         elems = 2.0 * Bq * N * D
         sm_mhz = line["clocks"].get("sm_mhz") or 1700
         fp32_peak = 148 * 128 * sm_mhz * 1e6                       # FP32 lane-instructions/s at the clock seen under load
-        line["linkpred"] = {"metric": "linkpred_queries_per_s", "value": Bq / (t * 1e-3), "unit": "queries/s", "ms": t, "queries": Bq,
-                            "candidates": N, "layers": 2, "candidate_distances_per_s": 2.0 * Bq * N / (t * 1e-3) / 2,
+        line["linkpred"] = {"metric": "linkpred_queries_per_s", "value": Bq * world / (t * 1e-3), "unit": "queries/s", "ms": t, "queries": Bq * world,
+                            "scaling": "weak",
+                            "candidates": N, "layers": 2, "candidate_distances_per_s": float(Bq) * world * N / (t * 1e-3),
                             "fp32_instr_per_s": 2 * elems / (t * 1e-3), "frac_fp32_pipe": 2 * elems / (t * 1e-3) / fp32_peak,
                             "bound": "fp32 CUDA cores (2 instr / candidate feature), not HBM"}
         del tabs_e, tabs_r
@@ -419,10 +439,21 @@ def run_b200(args):
 
         copy_stream = torch.cuda.Stream(device=dev)
 
+        trace = os.environ.get("JMAC_BENCH_TRACE") == "1"      # phase times of the host-fed step on stderr (rank 0)
+
         def e2e_step():
+            marks = []
+
+            def mark(name):
+                if trace:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    marks.append((name, ev))
             JF.clear_plan_cache()
             main = torch.cuda.current_stream()
+            mark("start")
             dei, det = h_ei.to(dev, non_blocking=True), h_et.to(dev, non_blocking=True)      # the plan needs the edges first
+            mark("edges_h2d")
             dx, dr = torch.empty_like(h_x, device=dev), torch.empty_like(h_r, device=dev)    # owned by the main stream's pool
             copy_stream.wait_stream(main)
             with torch.cuda.stream(copy_stream):                                              # tables upload while the plan is built
@@ -432,7 +463,9 @@ def run_b200(args):
                 JF.get_plan(dei, det, N, R + 1)
             else:
                 runner.plan = JF.GraphPlan(dei, det, n_loc, R + 1, n_src=n_src)
+            mark("plan")
             main.wait_stream(copy_stream)
+            mark("tables_h2d_wait")
             dx.requires_grad_(True)
             dr.requires_grad_(True)
             for p in params:
@@ -441,13 +474,19 @@ def run_b200(args):
                 h = layers[1](layers[0](dx, dr, dei, det), dr, dei, det)
             else:
                 h = runner.forward(dx, dr)
+            mark("forward")
             loss = (h * g_loc).sum()
             loss.backward()
+            mark("backward")
             if not single:
                 JD.all_reduce_grads(runner.replicated + [dr], dist.group.WORLD)
                 loss = loss.detach().clone()
                 dist.all_reduce(loss)
-            return float(loss.item())
+                mark("all_reduce")
+            out = float(loss.item())
+            if trace and rank == 0:
+                print("e2e phases [ms]: " + ", ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.1f}" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+            return out
         try:
             e2e_step()
         except Exception as ex:                      # keep the device-timed line even if the host-fed path fails

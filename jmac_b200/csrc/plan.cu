@@ -31,6 +31,30 @@ int sm_count() {
     return n;
 }
 
+// Stream-ordered allocation for the plan and its build temporaries: cudaMalloc / cudaFree serialise the device and
+// cost milliseconds per 100 MB block, which made rebuilding a 40M-edge plan (a triple-transfer round, train.py:471-472,
+// or the host-fed bench step) slower than the sorts themselves.  The default memory pool keeps freed blocks
+// (release threshold = max), so a rebuilt plan reuses the memory of the destroyed one without touching the OS.
+static void pool_setup() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+}
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t bytes, cudaStream_t st) {
+    pool_setup();
+    return cudaMallocAsync(reinterpret_cast<void**>(p), bytes > 0 ? bytes : 1, st);
+}
+static void dfree(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
 int plan_scratch(jmac_plan* p, size_t bytes, float** out) {
     if (bytes > p->scratch_bytes) {
         if (p->scratch) JMAC_CUDA(cudaFree(p->scratch));
@@ -141,8 +165,8 @@ static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cuda
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
     size_t nb = sizeof(int) * (size_t)(nseg + 1);
-    JMAC_CUDA(cudaMalloc(&n_it, nb)); JMAC_CUDA(cudaMalloc(&n_sl, nb)); JMAC_CUDA(cudaMalloc(&n_sp, nb));
-    JMAC_CUDA(cudaMalloc(&o_it, nb)); JMAC_CUDA(cudaMalloc(&o_sl, nb)); JMAC_CUDA(cudaMalloc(&o_sp, nb));
+    JMAC_CUDA(dmalloc(&n_it, nb, st)); JMAC_CUDA(dmalloc(&n_sl, nb, st)); JMAC_CUDA(dmalloc(&n_sp, nb, st));
+    JMAC_CUDA(dmalloc(&o_it, nb, st)); JMAC_CUDA(dmalloc(&o_sl, nb, st)); JMAC_CUDA(dmalloc(&o_sp, nb, st));
     JMAC_CUDA(cudaMemsetAsync(n_it, 0, nb, st)); JMAC_CUDA(cudaMemsetAsync(n_sl, 0, nb, st)); JMAC_CUDA(cudaMemsetAsync(n_sp, 0, nb, st));
     int threads = 256, blocks = (nseg + threads - 1) / threads;
     if (nseg > 0) {
@@ -151,7 +175,7 @@ static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cuda
     }
     // exclusive scans over nseg+1 entries (last entry of the counts is 0) -> totals land at [nseg]
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, n_it, o_it, nseg + 1, st));
-    JMAC_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    JMAC_CUDA(dmalloc(&tmp, tmp_bytes, st));
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_it, o_it, nseg + 1, st));
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_sl, o_sl, nseg + 1, st));
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_sp, o_sp, nseg + 1, st));
@@ -161,14 +185,13 @@ static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cuda
     JMAC_CUDA(cudaMemcpyAsync(&tot[2], o_sp + nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
     JMAC_CUDA(cudaStreamSynchronize(st));
     out->n_items = tot[0]; out->n_slots = tot[1]; out->n_splits = tot[2];
-    JMAC_CUDA(cudaMalloc(&out->items, sizeof(Item) * (size_t)(tot[0] > 0 ? tot[0] : 1)));
-    JMAC_CUDA(cudaMalloc(&out->splits, sizeof(Split) * (size_t)(tot[2] > 0 ? tot[2] : 1)));
+    JMAC_CUDA(dmalloc(&out->items, sizeof(Item) * (size_t)(tot[0] > 0 ? tot[0] : 1), st));
+    JMAC_CUDA(dmalloc(&out->splits, sizeof(Split) * (size_t)(tot[2] > 0 ? tot[2] : 1), st));
     if (nseg > 0) {
         item_fill_kernel<<<blocks, threads, 0, st>>>(ptr, nseg, chunk, n_it, o_it, o_sl, o_sp, out->items, out->splits);
         JMAC_LAUNCH_CHECK();
     }
-    JMAC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(n_it); cudaFree(n_sl); cudaFree(n_sp); cudaFree(o_it); cudaFree(o_sl); cudaFree(o_sp); cudaFree(tmp);
+    dfree(n_it, st); dfree(n_sl, st); dfree(n_sp, st); dfree(o_it, st); dfree(o_sl, st); dfree(o_sp, st); dfree(tmp, st);
     return 0;
 }
 
@@ -176,15 +199,14 @@ static int sort_by_int_key(const int* keys_in, int64_t E, int end_bit, cudaStrea
     int* iota = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    JMAC_CUDA(cudaMalloc(&iota, sizeof(int) * (size_t)(E > 0 ? E : 1)));
+    JMAC_CUDA(dmalloc(&iota, sizeof(int) * (size_t)(E > 0 ? E : 1), st));
     int threads = 256;
     int64_t blocks = (E + threads - 1) / threads;
     if (E > 0) { iota_kernel<<<(unsigned)blocks, threads, 0, st>>>(iota, E); JMAC_LAUNCH_CHECK(); }
     JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned*)keys_in, (unsigned*)keys_out, iota, pos_out, (int)E, 0, end_bit, st));
-    JMAC_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+    JMAC_CUDA(dmalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1, st));
     JMAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned*)keys_in, (unsigned*)keys_out, iota, pos_out, (int)E, 0, end_bit, st));
-    JMAC_CUDA(cudaStreamSynchronize(st));
-    cudaFree(iota); cudaFree(tmp);
+    dfree(iota, st); dfree(tmp, st);
     return 0;
 }
 
@@ -198,13 +220,14 @@ extern "C" uint64_t jmac_launch_count(void) { return __atomic_load_n(&jmac::g_la
 
 extern "C" int jmac_plan_destroy(jmac_plan* p) {
     if (!p) return 0;
-    cudaFree(p->rowptr); cudaFree(p->csr_src); cudaFree(p->csr_type); cudaFree(p->csr_eid); cudaFree(p->csr_dst);
-    cudaFree(p->sqrt_deg); cudaFree(p->colptr); cudaFree(p->csc_pos); cudaFree(p->csc_dst);
-    cudaFree(p->typptr); cudaFree(p->typ_pos); cudaFree(p->typ_dst);
-    cudaFree(p->dst_items.items); cudaFree(p->dst_items.splits);
-    cudaFree(p->src_items.items); cudaFree(p->src_items.splits);
-    cudaFree(p->typ_items.items); cudaFree(p->typ_items.splits);
-    cudaFree(p->scratch);
+    // One device-wide wait (any stream may still be reading the plan), then stream-ordered frees back into the pool:
+    // the ~20 cudaFree calls this replaces each synchronised the device and returned the memory to the OS.
+    cudaDeviceSynchronize();
+    void* ptrs[] = {p->rowptr, p->csr_src, p->csr_type, p->csr_eid, p->csr_dst, p->sqrt_deg, p->colptr, p->csc_pos, p->csc_dst, p->typptr,
+                    p->typ_pos, p->typ_dst, p->dst_items.items, p->dst_items.splits, p->src_items.items, p->src_items.splits,
+                    p->typ_items.items, p->typ_items.splits};
+    for (void* q : ptrs) dfree(q, 0);
+    if (p->scratch) cudaFree(p->scratch);
     delete p;
     return 0;
 }
@@ -213,20 +236,20 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
     const int64_t E = p->E, N = p->N, NS = p->N_src, R = p->n_rel;
     const size_t Eb = (size_t)(E > 0 ? E : 1);
     const int tb = bits_for(R), nbits = bits_for(N), sbits = bits_for(NS);
-    JMAC_CUDA(cudaMalloc(&p->rowptr, sizeof(int) * (size_t)(N + 1)));
-    JMAC_CUDA(cudaMalloc(&p->colptr, sizeof(int) * (size_t)(NS + 1)));
-    JMAC_CUDA(cudaMalloc(&p->typptr, sizeof(int) * (size_t)(R + 1)));
-    JMAC_CUDA(cudaMalloc(&p->sqrt_deg, sizeof(float) * (size_t)(N > 0 ? N : 1)));
-    JMAC_CUDA(cudaMalloc(&p->csr_src, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csr_type, sizeof(int) * Eb));
-    JMAC_CUDA(cudaMalloc(&p->csr_eid, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csr_dst, sizeof(int) * Eb));
-    JMAC_CUDA(cudaMalloc(&p->csc_pos, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->csc_dst, sizeof(int) * Eb));
-    JMAC_CUDA(cudaMalloc(&p->typ_pos, sizeof(int) * Eb)); JMAC_CUDA(cudaMalloc(&p->typ_dst, sizeof(int) * Eb));
+    JMAC_CUDA(dmalloc(&p->rowptr, sizeof(int) * (size_t)(N + 1), st));
+    JMAC_CUDA(dmalloc(&p->colptr, sizeof(int) * (size_t)(NS + 1), st));
+    JMAC_CUDA(dmalloc(&p->typptr, sizeof(int) * (size_t)(R + 1), st));
+    JMAC_CUDA(dmalloc(&p->sqrt_deg, sizeof(float) * (size_t)(N > 0 ? N : 1), st));
+    JMAC_CUDA(dmalloc(&p->csr_src, sizeof(int) * Eb, st)); JMAC_CUDA(dmalloc(&p->csr_type, sizeof(int) * Eb, st));
+    JMAC_CUDA(dmalloc(&p->csr_eid, sizeof(int) * Eb, st)); JMAC_CUDA(dmalloc(&p->csr_dst, sizeof(int) * Eb, st));
+    JMAC_CUDA(dmalloc(&p->csc_pos, sizeof(int) * Eb, st)); JMAC_CUDA(dmalloc(&p->csc_dst, sizeof(int) * Eb, st));
+    JMAC_CUDA(dmalloc(&p->typ_pos, sizeof(int) * Eb, st)); JMAC_CUDA(dmalloc(&p->typ_dst, sizeof(int) * Eb, st));
 
     const int threads = 256;
     const unsigned eblocks = (unsigned)((E + threads - 1) / threads);
     const unsigned e1blocks = (unsigned)((E + 1 + threads - 1) / threads);
     int* flags = nullptr;  // [0] = bad index flag, [1] = max degree
-    JMAC_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
+    JMAC_CUDA(dmalloc(&flags, 2 * sizeof(int), st));
     JMAC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
 
     // ---- by destination, secondary key relation type
@@ -235,14 +258,14 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         int* v_in = nullptr;
         void* tmp = nullptr;
         size_t tmp_bytes = 0;
-        JMAC_CUDA(cudaMalloc(&k_in, sizeof(uint64_t) * Eb)); JMAC_CUDA(cudaMalloc(&k_out, sizeof(uint64_t) * Eb));
-        JMAC_CUDA(cudaMalloc(&v_in, sizeof(int) * Eb));
+        JMAC_CUDA(dmalloc(&k_in, sizeof(uint64_t) * Eb, st)); JMAC_CUDA(dmalloc(&k_out, sizeof(uint64_t) * Eb, st));
+        JMAC_CUDA(dmalloc(&v_in, sizeof(int) * Eb, st));
         if (E > 0) {
             make_keys_kernel<<<eblocks, threads, 0, st>>>(d_row, d_col, d_type, E, N, NS, R, tb, k_in, v_in, flags);
             JMAC_LAUNCH_CHECK();
         }
         JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
-        JMAC_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
+        JMAC_CUDA(dmalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1, st));
         JMAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
         if (E > 0) {
             fill_csr_kernel<<<eblocks, threads, 0, st>>>(k_out, p->csr_eid, d_col, E, tb, p->csr_src, p->csr_type, p->csr_dst);
@@ -251,9 +274,9 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         int bad = 0;
         JMAC_CUDA(cudaMemcpyAsync(&bad, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         JMAC_CUDA(cudaStreamSynchronize(st));
-        cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(tmp);
+        dfree(k_in, st); dfree(k_out, st); dfree(v_in, st); dfree(tmp, st);
         if (bad) {
-            cudaFree(flags);
+            dfree(flags, st);
             set_error("jmac_plan_create: edge_index / edge_type entry out of range (N=%lld, n_rel=%lld)", (long long)N, (long long)R);
             return JMAC_ERANGE;
         }
@@ -269,7 +292,7 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
     // ---- by source (stable: positions stay in destination order inside a source segment)
     {
         int* sorted = nullptr;
-        JMAC_CUDA(cudaMalloc(&sorted, sizeof(int) * Eb));
+        JMAC_CUDA(dmalloc(&sorted, sizeof(int) * Eb, st));
         int rc = sort_by_int_key(p->csr_src, E, sbits, st, sorted, p->csc_pos);
         if (rc) return rc;
         build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)NS, p->colptr);
@@ -281,10 +304,9 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)R, p->typptr);
         JMAC_LAUNCH_CHECK();
         if (E > 0) { gather_int_kernel<<<eblocks, threads, 0, st>>>(p->csr_dst, p->typ_pos, E, p->typ_dst); JMAC_LAUNCH_CHECK(); }
-        JMAC_CUDA(cudaStreamSynchronize(st));
-        cudaFree(sorted);
+        dfree(sorted, st);
     }
-    cudaFree(flags);
+    dfree(flags, st);
     int rc = build_items(p->rowptr, (int)N, p->chunk, 1, st, &p->dst_items);
     if (rc) return rc;
     rc = build_items(p->colptr, (int)NS, p->chunk, 1, st, &p->src_items);
@@ -309,6 +331,7 @@ extern "C" int jmac_plan_create_bipartite(const int64_t* d_row, const int64_t* d
     p->E = E; p->N = N_dst; p->N_src = N_src; p->n_rel = n_rel;
     p->chunk = chunk > 0 ? chunk : 256;
     int rc = plan_build(p, d_row, d_col, d_type, (cudaStream_t)stream);
+    if (rc == 0 && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = JMAC_EINVAL;   // complete on return: usable from any stream
     if (rc) { jmac_plan_destroy(p); return rc; }
     *out = p;
     return 0;
