@@ -210,12 +210,12 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Same computation with the row gathers moved off the register file: every warp owns a ring of
-// RING_S shared-memory slots; lane 0 issues one cp.async.bulk (TMA bulk copy, 1 instruction per row)
-// for each of Q[j], X[j], S[t], R'[t] of an edge into a slot and the whole warp waits on the slot's
-// mbarrier RING_S-1 edges later.  Memory latency is hidden by bytes in flight in shared memory
-// (12 warps x 7 slots x 2 KB per SM) instead of by occupancy; the LSU only sees conflict-free LDS.128.
-// The relation rows S[t], R'[t] are L2-resident: plain loads, prefetched one edge ahead in registers.
+// Same computation with the row gathers moved off the register file (the default): every warp owns a ring
+// of RING_S shared-memory slots; lane 0 issues one cp.async.bulk (TMA bulk copy, 1 instruction per row) for
+// each of Q[j], X[j] of an edge into a slot and the whole warp waits on the slot's mbarrier RING_S-1 edges
+// later.  Memory latency is hidden by bytes in flight in shared memory (16 warps x 6 slots x 2 KB = 192 KB
+// per SM) instead of by occupancy; the LSU only sees conflict-free LDS.128.  The relation rows S[t], R'[t]
+// are L2-resident: plain loads issued before the wait on the ring.
 // ------------------------------------------------------------------------------------------------
 constexpr int RING_S = 6, RING_ROWS = 2;   // slot = {Q[j], X[j]}; 16 warps x 6 x 2 KB = 192 KB at d = 256
 
@@ -479,15 +479,15 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     }
     if (p.n_items == 0) return 0;
     const int threads = 256;
-    // The bulk-copy ring variant measures the same as the register-staged kernel on C4 (17.6-18.9 ms vs
-    // 18.4 ms: the bound is the memory system's random-1KB-gather rate, not latency hiding -- DESIGN.md
-    // section 4), so the simpler kernel stays the default; JMAC_EDGE_RING=1 selects the ring.
+    // The bulk-copy ring kernel is the default (C4 forward: 15.9-16.6 ms against ~20 ms for the register-staged one,
+    // which can keep only ~64 KB of gathers in flight per SM -- DESIGN.md section 4); JMAC_EDGE_RING=0 selects the
+    // register-staged kernel, which is also the fallback when a ring of d-wide rows does not fit in shared memory.
     static const int use_ring = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
     const size_t ring_smem = (size_t)RING_WARPS * RING_S * (RING_ROWS * (size_t)d * 4 + 8);
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL == 1 ? 4 : 2;
         if (use_ring && plan->E > 0 && ring_smem <= 220 * 1024) {
-            // bulk-copy ring variant: one CTA of 12 warps per SM
+            // one CTA of RING_WARPS warps per SM
             auto kern = d == VPL * 128 ? edge_fwd_ring_kernel<VPL, true> : edge_fwd_ring_kernel<VPL, false>;
             JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
             long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
