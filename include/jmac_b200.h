@@ -143,6 +143,12 @@ int jmac_bn_tanh_bwd_apply(const float* gout, const float* out, const float* pre
  * ------------------------------------------------------------------------------------------ */
 int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
                      float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+/* Same product with up to two [M,N] addends folded into the epilogue, C = A.B^T + D1 (+ D2); D1/D2
+ * may alias C.  Fuses the gradient accumulation of the layer input (autograd's adds of
+ * dP W_top^T, dQ W_bot^T, the edge pass's dX and the self-loop term, src/jmac_model.py:49-52,75-76). */
+int jmac_gemm_tf32x3_add(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
+                         int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, const float* D1,
+                         const float* D2, int64_t ldd, void* stream);
 /* Weight-gradient product D[KO,N] = X[M,KO]^T . G[M,N] (reduction over the M node rows), same
  * 3xTF32 scheme with both operands split in shared memory; KO in {128,256}, N % 32 == 0, N <= 256.
  * Deterministic: per-CTA partials in `workspace` (jmac_gemm_tn_workspace_bytes) summed in order. */

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "jmac_bn_tanh_bwd_stats": (c_int, [P, P, P, c_int64, c_int, P, P, P, P]),
     "jmac_bn_tanh_bwd_apply": (c_int, [P, P, P, c_int64, c_int, P, P, P, P, c_int64, c_int, P, P, P, P]),
     "jmac_gemm_tf32x3": (c_int, [P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
+    "jmac_gemm_tf32x3_add": (c_int, [P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, c_int64, P]),
     "jmac_gemm_tn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "jmac_gemm_tn_tf32x3": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, P, P]),
     "jmac_transe_margin_fwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P]),

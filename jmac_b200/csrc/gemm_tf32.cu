@@ -48,6 +48,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void add_v8(float (&v)[8], const float* p) {
+    float r[8];
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] += r[q];
+}
+__device__ __forceinline__ void st_v8(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                 "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -83,6 +94,8 @@ struct GemmParams {
     int M, N, nkb;      // nkb = K / 16
     float* C;
     int ldc;
+    const float *D1, *D2;   // optional [M,N] addends of the epilogue (C = A.B^T + D1 + D2), leading dimension ldd; may alias C
+    int ldd;
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -195,6 +208,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int row = mb * G_BM + half * 128 + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 256;
             float* crow = p.C + (size_t)row * p.ldc;
+            const float* d1row = p.D1 ? p.D1 + (size_t)row * p.ldd : nullptr;
+            const float* d2row = p.D2 ? p.D2 + (size_t)row * p.ldd : nullptr;
             uint32_t raw[2][32];
             const int nchunk = p.N / 32;               // N % 32 == 0 enforced by the host
             tc_ld32_issue(taddr, raw[0]);
@@ -204,11 +219,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     tc_ld_wait();
                     if (c + 1 < nchunk) tc_ld32_issue(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
                     if (row < p.M) {
+                        // 256-bit accesses (sm_100): every request of a lane is one full 32-byte sector of its own row
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 v = make_float4(__uint_as_float(raw[c & 1][4 * j]), __uint_as_float(raw[c & 1][4 * j + 1]),
-                                                   __uint_as_float(raw[c & 1][4 * j + 2]), __uint_as_float(raw[c & 1][4 * j + 3]));
-                            reinterpret_cast<float4*>(crow + c * 32)[j] = v;
+                        for (int j = 0; j < 4; ++j) {
+                            float v[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(raw[c & 1][8 * j + q]);
+                            // gradient accumulation fused into the epilogue (each thread reads the addend chunk it overwrites)
+                            if (d1row) add_v8(v, d1row + c * 32 + 8 * j);
+                            if (d2row) add_v8(v, d2row + c * 32 + 8 * j);
+                            st_v8(crow + c * 32 + 8 * j, v);
                         }
                     }
                 }
@@ -466,10 +486,17 @@ extern "C" int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, 
 
 extern "C" int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C, int64_t ldc,
                                 int64_t M, int N, int K, void* stream) {
+    return jmac_gemm_tf32x3_add(A, lda, B_hi, B_lo, ldb, C, ldc, M, N, K, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int jmac_gemm_tf32x3_add(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C, int64_t ldc,
+                                    int64_t M, int N, int K, const float* D1, const float* D2, int64_t ldd, void* stream) {
     JMAC_ARG(A && B_hi && B_lo && C && M > 0 && M < (int64_t(1) << 31));
+    JMAC_ARG(D2 == nullptr || D1 != nullptr);
+    JMAC_ARG(D1 == nullptr || (ldd >= N && (ldd % 8) == 0 && ((uintptr_t)D1 % 32) == 0 && ((uintptr_t)D2 % 32) == 0));
     JMAC_ARG(N >= 32 && N <= 256 && (N % 32) == 0 && K >= 16 && (K % 16) == 0);
-    JMAC_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0);
-    JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)B_lo % 16) == 0 && ((uintptr_t)C % 16) == 0);
+    JMAC_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 8) == 0);      // C, D: 256-bit row accesses
+    JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)B_lo % 16) == 0 && ((uintptr_t)C % 32) == 0);
     CUtensorMap map_a, map_bhi, map_blo;
     int rc = make_map_f32(&map_a, A, M, K, lda, G_BM);
     if (rc) return rc;
@@ -479,6 +506,7 @@ extern "C" int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, 
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = N; p.nkb = K / G_BK; p.C = C; p.ldc = (int)ldc;
+    p.D1 = D1; p.D2 = D2; p.ldd = (int)ldd;
     const int n_mb = (int)((M + G_BM - 1) / G_BM);
     const int grid = n_mb < sm_count() ? n_mb : sm_count();
     JMAC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));

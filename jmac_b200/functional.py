@@ -209,6 +209,80 @@ def edge_phase(plan, P, Q, X, S, Rp, a_att, slope, Xself=None):
     return EdgePhaseFn.apply(plan, P, Q, X, S, Rp, a_att, slope, Xself)
 
 
+class AttnEdgeFn(torch.autograd.Function):
+    """The layer-input part of RelationAwareLayer.forward in one autograd node (single GPU, comp_op='sub'):
+    ``P = X W_top, Q = X W_bot, S = R' W_bot`` and the edge phase with the fused self loop, returning
+    ``T = agg + X - R'[loop]``.  Same kernels as ``node_mm`` + ``edge_phase``; what the fusion buys is the backward:
+    ``dX = dP W_top^T + dQ W_bot^T + dXe + dT`` is accumulated in the epilogues of the two input-gradient GEMMs
+    instead of three elementwise passes over [N,d] by autograd."""
+
+    @staticmethod
+    def forward(ctx, plan: GraphPlan, X, W_att, Rp, a_att, slope: float):
+        _need_cuda(X, W_att, Rp, a_att)
+        lib = _lib.load()
+        X, W_att, Rp, a = _f32c(X), _f32c(W_att), _f32c(Rp), _f32c(a_att.reshape(-1))
+        N, d = X.shape
+        if N != plan.N or plan.N_src != plan.N or Rp.shape[0] != plan.n_rel:
+            raise ValueError("table sizes do not match the graph plan")
+        Wt, Wb = W_att[:d], W_att[d:]
+        P = gemm_nt(X, Wt.t().contiguous())
+        Q = gemm_nt(X, Wb.t().contiguous())
+        S = Rp @ Wb
+        agg = torch.empty_like(X)
+        T = torch.empty_like(X)
+        lse = torch.empty(N, dtype=torch.float32, device=X.device)
+        need_grad = any(ctx.needs_input_grad)
+        erec = torch.empty(max(plan.E, 1) * int(lib.jmac_edge_record_bytes(d)), dtype=torch.uint8, device=X.device) if need_grad else None
+        with torch.cuda.device(X.device):
+            check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
+                                          ptr(X), ptr(T), ptr(erec), stream_ptr()), "jmac_edge_fwd")
+        ctx.plan, ctx.slope, ctx.a_shape = plan, float(slope), a_att.shape
+        if need_grad:
+            ctx.save_for_backward(X, W_att, Rp, a, P, Q, S, agg, lse, erec)
+        return T
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        X, W_att, Rp, a, P, Q, S, agg, lse, erec = ctx.saved_tensors
+        plan, slope = ctx.plan, ctx.slope
+        N, d = X.shape
+        G = _f32c(g)
+        dev = X.device
+        Wt, Wb = W_att[:d], W_att[d:]
+        dP, dXe, dQ = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+        dRp, dS = torch.empty_like(Rp), torch.empty_like(S)
+        da = torch.zeros(d, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr()
+            check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(X), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
+                                        ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
+            check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
+                  "jmac_edge_bwd_src")
+            check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st),
+                  "jmac_edge_bwd_rel")
+        dRp[-1] -= G.sum(0)                                   # T = agg + X - Rp[-1]
+        dRp += dS @ Wb.t()                                    # S = Rp Wb
+        dX = dW = None
+        if ctx.needs_input_grad[1]:
+            dX = gemm_nt(dP, Wt.contiguous(), add1=dXe, add2=G, out=dXe)        # dP Wt^T + dXe + dT, in place over dXe
+            dX = gemm_nt(dQ, Wb.contiguous(), add1=dX, out=dX)                   # + dQ Wb^T
+        if ctx.needs_input_grad[2]:
+            dWt = gemm_tn(X, dP)
+            dWb = gemm_tn(X, dQ)
+            dWb += Rp.t() @ dS
+            dW = torch.cat([dWt, dWb], dim=0)
+        return None, dX, dW, dRp, da.view(ctx.a_shape), None
+
+
+def attn_edge_eligible(X: torch.Tensor, d: int) -> bool:
+    return X.is_cuda and X.dtype == torch.float32 and _tc_eligible(X.shape[0], d, d) and _tn_eligible(X.shape[0], d, d)
+
+
+def attn_edge(plan, X, W_att, Rp, a_att, slope):
+    return AttnEdgeFn.apply(plan, X, W_att, Rp, a_att, slope)
+
+
 # ----------------------------------------------------------------------------------------------
 # node-level dense products (3xTF32 on tcgen05, fp32-accurate)
 # ----------------------------------------------------------------------------------------------
@@ -219,17 +293,24 @@ def _split_tf32(w_nk: torch.Tensor):
     return hi, w_nk - hi
 
 
-def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor) -> torch.Tensor:
-    """C[M,N] = A[M,K] @ B_nk[N,K]^T through jmac_gemm_tf32x3 (raises on unsupported shapes)."""
+def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ B_nk[N,K]^T (+ add1 + add2) through jmac_gemm_tf32x3_add (raises on unsupported shapes).
+    ``add1``/``add2``: [M,N] contiguous addends folded into the epilogue; ``out`` may be one of them (in-place accumulate)."""
     lib = _lib.load()
     _need_cuda(A, B_nk)
     A, B_nk = _f32c(A), _f32c(B_nk)
     M, K = A.shape
     N = B_nk.shape[0]
     hi, lo = _split_tf32(B_nk)
-    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    C = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=A.device)
+    for t in (add1, add2, out):
+        if t is not None and (t.shape != (M, N) or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("addends / out must be contiguous float32 [M,N]")
+    if add1 is None and add2 is not None:
+        add1, add2 = add2, None
     with torch.cuda.device(A.device):
-        check(lib.jmac_gemm_tf32x3(ptr(A), K, ptr(hi), ptr(lo), K, ptr(C), N, M, N, K, stream_ptr()), "jmac_gemm_tf32x3")
+        check(lib.jmac_gemm_tf32x3_add(ptr(A), K, ptr(hi), ptr(lo), K, ptr(C), N, M, N, K, ptr(add1), ptr(add2), N, stream_ptr()),
+              "jmac_gemm_tf32x3_add")
     return C
 
 

@@ -78,10 +78,15 @@ class RelationAwareLayer(nn.Module):
         Rp = self.relation_transform(rel_emb)                                    # [nr+1, d]; row nr = self loop
         plan = JF.get_plan(edge_index, edge_type, num_ent, Rp.size(0))
         X = ent_emb.contiguous()
-        P = JF.node_mm(X, self.w_att[:d])           # node tables: 3xTF32 tcgen05 GEMM (fp32-accurate), small ones: library
-        Q = JF.node_mm(X, self.w_att[d:])
-        S = torch.mm(Rp, self.w_att[d:])
-        T = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope, X)  # agg + X - R'[loop] (self-loop fused)
+        if JF.attn_edge_eligible(X, d):
+            # large node tables: one autograd node for the attention inputs + edge phase, so that the input gradient
+            # dP W_top^T + dQ W_bot^T + dXe + dT is accumulated in GEMM epilogues instead of elementwise passes
+            T = JF.attn_edge(plan, X, self.w_att, Rp, self.a_att, self.leaky_slope)
+        else:
+            P = JF.node_mm(X, self.w_att[:d])       # node tables: 3xTF32 tcgen05 GEMM (fp32-accurate), small ones: library
+            Q = JF.node_mm(X, self.w_att[d:])
+            S = torch.mm(Rp, self.w_att[d:])
+            T = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope, X)  # agg + X - R'[loop] (self-loop fused)
         pre = JF.node_mm(T, self.gcn_weight * 0.5)                               # (neigh + self)/2, :49-52
         training = self.training or not self.bn.track_running_stats
         if self.training and self.bn.track_running_stats:
