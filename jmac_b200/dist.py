@@ -183,11 +183,17 @@ def sharded_layer_forward(layer, x_loc, rel_emb, shard: Shard, plan, group, ops=
     # dXe + dQ W_bot^T on the partials BEFORE the single reduce-scatter (linearity).  The all-gather is
     # asynchronous and overlaps the local P GEMM.
     Xf = GatherRowsFn.apply(x_loc, shard, group, x_full)
-    P = mm(x_loc, layer.w_att[:d])
-    S = torch.mm(Rp, layer.w_att[d:])
-    wait_gather(Xf)
-    Qf = mm(Xf, layer.w_att[d:])
-    T = ops.edge_phase(plan, P, Qf, Xf, S, Rp, layer.a_att, layer.leaky_slope, x_loc)     # self-loop term fused
+    fused = getattr(ops, "attn_edge", None)
+    if fused is not None and ops.attn_edge_eligible(x_loc, d) and ops.attn_edge_eligible(Xf, d):
+        # one autograd node: dQ W_bot^T + dXe (the reduce-scattered partial) and dP W_top^T + dT come out of GEMM epilogues
+        wait_gather(Xf)
+        T = fused(plan, x_loc, layer.w_att, Rp, layer.a_att, layer.leaky_slope, Xf)
+    else:
+        P = mm(x_loc, layer.w_att[:d])
+        S = torch.mm(Rp, layer.w_att[d:])
+        wait_gather(Xf)
+        Qf = mm(Xf, layer.w_att[d:])
+        T = ops.edge_phase(plan, P, Qf, Xf, S, Rp, layer.a_att, layer.leaky_slope, x_loc)     # self-loop term fused
     pre = mm(T, layer.gcn_weight * 0.5)
     training = layer.training or not layer.bn.track_running_stats
     if layer.training and layer.bn.track_running_stats:

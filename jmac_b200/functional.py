@@ -210,77 +210,87 @@ def edge_phase(plan, P, Q, X, S, Rp, a_att, slope, Xself=None):
 
 
 class AttnEdgeFn(torch.autograd.Function):
-    """The layer-input part of RelationAwareLayer.forward in one autograd node (single GPU, comp_op='sub'):
-    ``P = X W_top, Q = X W_bot, S = R' W_bot`` and the edge phase with the fused self loop, returning
-    ``T = agg + X - R'[loop]``.  Same kernels as ``node_mm`` + ``edge_phase``; what the fusion buys is the backward:
-    ``dX = dP W_top^T + dQ W_bot^T + dXe + dT`` is accumulated in the epilogues of the two input-gradient GEMMs
-    instead of three elementwise passes over [N,d] by autograd."""
+    """The layer-input part of RelationAwareLayer.forward in one autograd node (comp_op='sub'):
+    ``P = Xd W_top, Q = Xs W_bot, S = R' W_bot`` and the edge phase with the fused self loop, returning
+    ``T = agg + Xd - R'[loop]``.  ``Xd`` are the destination rows, ``Xs`` the source table (``None``: the same table,
+    single GPU; destination-sharded: the all-gathered table).  Same kernels as ``node_mm`` + ``edge_phase``; what the
+    fusion buys is the backward: ``dXd = dP W_top^T + dT`` and ``dXs = dQ W_bot^T + dXe`` (one sum when the tables
+    coincide) are accumulated in the epilogues of the input-gradient GEMMs instead of elementwise passes by autograd."""
 
     @staticmethod
-    def forward(ctx, plan: GraphPlan, X, W_att, Rp, a_att, slope: float):
-        _need_cuda(X, W_att, Rp, a_att)
+    def forward(ctx, plan: GraphPlan, Xd, Xs, W_att, Rp, a_att, slope: float):
+        same = Xs is None
+        _need_cuda(Xd, W_att, Rp, a_att)
         lib = _lib.load()
-        X, W_att, Rp, a = _f32c(X), _f32c(W_att), _f32c(Rp), _f32c(a_att.reshape(-1))
-        N, d = X.shape
-        if N != plan.N or plan.N_src != plan.N or Rp.shape[0] != plan.n_rel:
+        Xd, W_att, Rp, a = _f32c(Xd), _f32c(W_att), _f32c(Rp), _f32c(a_att.reshape(-1))
+        Xs = Xd if same else _f32c(Xs)
+        N, d = Xd.shape
+        if N != plan.N or Xs.shape[0] != plan.N_src or Rp.shape[0] != plan.n_rel:
             raise ValueError("table sizes do not match the graph plan")
         Wt, Wb = W_att[:d], W_att[d:]
-        P = gemm_nt(X, Wt.t().contiguous())
-        Q = gemm_nt(X, Wb.t().contiguous())
+        P = gemm_nt(Xd, Wt.t().contiguous())
+        Q = gemm_nt(Xs, Wb.t().contiguous())
         S = Rp @ Wb
-        agg = torch.empty_like(X)
-        T = torch.empty_like(X)
-        lse = torch.empty(N, dtype=torch.float32, device=X.device)
+        agg = torch.empty_like(Xd)
+        T = torch.empty_like(Xd)
+        lse = torch.empty(N, dtype=torch.float32, device=Xd.device)
         need_grad = any(ctx.needs_input_grad)
-        erec = torch.empty(max(plan.E, 1) * int(lib.jmac_edge_record_bytes(d)), dtype=torch.uint8, device=X.device) if need_grad else None
-        with torch.cuda.device(X.device):
-            check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
-                                          ptr(X), ptr(T), ptr(erec), stream_ptr()), "jmac_edge_fwd")
-        ctx.plan, ctx.slope, ctx.a_shape = plan, float(slope), a_att.shape
+        erec = torch.empty(max(plan.E, 1) * int(lib.jmac_edge_record_bytes(d)), dtype=torch.uint8, device=Xd.device) if need_grad else None
+        with torch.cuda.device(Xd.device):
+            check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(Xs), ptr(S), ptr(Rp), ptr(a), float(slope), d, ptr(agg), ptr(lse),
+                                          ptr(Xd), ptr(T), ptr(erec), stream_ptr()), "jmac_edge_fwd")
+        ctx.plan, ctx.slope, ctx.a_shape, ctx.same = plan, float(slope), a_att.shape, same
         if need_grad:
-            ctx.save_for_backward(X, W_att, Rp, a, P, Q, S, agg, lse, erec)
+            ctx.save_for_backward(Xd, Xs, W_att, Rp, a, P, Q, S, agg, lse, erec)
         return T
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        X, W_att, Rp, a, P, Q, S, agg, lse, erec = ctx.saved_tensors
-        plan, slope = ctx.plan, ctx.slope
-        N, d = X.shape
+        Xd, Xs, W_att, Rp, a, P, Q, S, agg, lse, erec = ctx.saved_tensors
+        plan, slope, same = ctx.plan, ctx.slope, ctx.same
+        d = Xd.shape[1]
         G = _f32c(g)
-        dev = X.device
+        dev = Xd.device
         Wt, Wb = W_att[:d], W_att[d:]
-        dP, dXe, dQ = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+        dP, dXe, dQ = torch.empty_like(Xd), torch.empty_like(Xs), torch.empty_like(Xs)
         dRp, dS = torch.empty_like(Rp), torch.empty_like(S)
         da = torch.zeros(d, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             st = stream_ptr()
-            check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(X), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
+            check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Xs), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
                                         ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
             check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
                   "jmac_edge_bwd_src")
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st),
                   "jmac_edge_bwd_rel")
-        dRp[-1] -= G.sum(0)                                   # T = agg + X - Rp[-1]
+        dRp[-1] -= G.sum(0)                                   # T = agg + Xd - Rp[-1]
         dRp += dS @ Wb.t()                                    # S = Rp Wb
-        dX = dW = None
-        if ctx.needs_input_grad[1]:
-            dX = gemm_nt(dP, Wt.contiguous(), add1=dXe, add2=G, out=dXe)        # dP Wt^T + dXe + dT, in place over dXe
-            dX = gemm_nt(dQ, Wb.contiguous(), add1=dX, out=dX)                   # + dQ Wb^T
-        if ctx.needs_input_grad[2]:
-            dWt = gemm_tn(X, dP)
-            dWb = gemm_tn(X, dQ)
+        dXd = dXs = dW = None
+        if same:
+            if ctx.needs_input_grad[1]:
+                dXd = gemm_nt(dP, Wt.contiguous(), add1=dXe, add2=G, out=dXe)    # dP Wt^T + dXe + dT, in place over dXe
+                dXd = gemm_nt(dQ, Wb.contiguous(), add1=dXd, out=dXd)             # + dQ Wb^T
+        else:
+            if ctx.needs_input_grad[1]:
+                dXd = gemm_nt(dP, Wt.contiguous(), add1=G)                        # dP Wt^T + dT
+            if ctx.needs_input_grad[2]:
+                dXs = gemm_nt(dQ, Wb.contiguous(), add1=dXe, out=dXe)             # dQ Wb^T + dXe: the partial that is reduce-scattered
+        if ctx.needs_input_grad[3]:
+            dWt = gemm_tn(Xd, dP)
+            dWb = gemm_tn(Xs, dQ)
             dWb += Rp.t() @ dS
             dW = torch.cat([dWt, dWb], dim=0)
-        return None, dX, dW, dRp, da.view(ctx.a_shape), None
+        return None, dXd, dXs, dW, dRp, da.view(ctx.a_shape), None
 
 
 def attn_edge_eligible(X: torch.Tensor, d: int) -> bool:
     return X.is_cuda and X.dtype == torch.float32 and _tc_eligible(X.shape[0], d, d) and _tn_eligible(X.shape[0], d, d)
 
 
-def attn_edge(plan, X, W_att, Rp, a_att, slope):
-    return AttnEdgeFn.apply(plan, X, W_att, Rp, a_att, slope)
+def attn_edge(plan, X, W_att, Rp, a_att, slope, X_src=None):
+    """T = agg + X - R'[loop] for destination rows ``X`` (sources: ``X_src``, default the same table)."""
+    return AttnEdgeFn.apply(plan, X, X_src, W_att, Rp, a_att, slope)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -69,5 +69,7 @@ def _worker(rank, world, port, N, E, R, d):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_encoder_matches_single_gpu_nccl():
-    mp.spawn(_worker, args=(2, _free_port(), 5000, 60000, 30, 256), nprocs=2, join=True)
+@pytest.mark.parametrize("N,E", [(5000, 60000),          # shards below 4096 rows: composed path (library GEMMs for the local rows)
+                                 (12000, 100001)])       # shards of ~6000 rows: the fused attention-input node on a gathered source table
+def test_sharded_encoder_matches_single_gpu_nccl(N, E):
+    mp.spawn(_worker, args=(2, _free_port(), N, E, 30, 256), nprocs=2, join=True)
