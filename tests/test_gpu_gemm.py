@@ -56,3 +56,24 @@ def test_node_mm_autograd_matches_torch():
     x2 = torch.randn(100, 300, device="cuda")
     w2 = torch.randn(300, 300, device="cuda")
     assert torch.equal(JF.node_mm(x2, w2), torch.mm(x2, w2))
+
+
+@pytest.mark.parametrize("M,K,N", [(5000, 256, 256), (4321, 128, 96), (513, 64, 32)])
+def test_gemm_epilogue_addends_and_in_place_accumulate(M, K, N):
+    """jmac_gemm_tf32x3_add: C = A B^T + D1 + D2 with 256-bit epilogue accesses; D1 may alias C (gradient accumulation)."""
+    from jmac_b200 import functional as JF
+    torch.manual_seed(M)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda") * 0.3
+    D1, D2 = torch.randn(M, N, device="cuda"), torch.randn(M, N, device="cuda") * 3
+    ref = A.double() @ B.double().t() + D1.double() + D2.double()
+    bound = A.double().abs() @ B.double().abs().t() + D1.double().abs() + D2.double().abs()
+    C = JF.gemm_nt(A, B, add1=D1, add2=D2)
+    assert float(((C.double() - ref).abs() / bound).max()) < 2e-6
+    acc = D1.clone()
+    out = JF.gemm_nt(A, B, add1=acc, add2=D2, out=acc)                 # in place over the first addend
+    assert out.data_ptr() == acc.data_ptr() and torch.equal(acc, C)
+    only2 = JF.gemm_nt(A, B, add2=D2)                                   # a single addend given as the second
+    assert float(((only2.double() - (ref - D1.double())).abs() / bound).max()) < 2e-6
+    with pytest.raises(ValueError):
+        JF.gemm_nt(A, B, add1=D1[:, : N // 2])
