@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
 // gathers in flight per SM (d = 256) -- the register-staged kernels above top out at ~64 KB, which Little's
 // law (2-2.7 us loaded latency) turns into ~4.5 TB/s.
 // ------------------------------------------------------------------------------------------------
-constexpr int BWD_RING_S = 12;
+// ring depth by row width: 12 slots of 1 KB + mask at d <= 256, 7 / 6 for the wider rows of VPL = 3 / 4
+template <int VPL> struct BwdRing { static constexpr int S = VPL <= 2 ? 12 : (VPL == 3 ? 7 : 6); };
 
+template <int BWD_RING_S>
 struct Ring {
     uint8_t* slots;
     uint32_t slots_s, bars, row_bytes, mask_b, slot_bytes;
@@ -389,7 +391,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
-    Ring ring;
+    constexpr int BWD_RING_S = BwdRing<VPL>::S;
+    Ring<BWD_RING_S> ring;
     ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
     Row<VPL> av, da_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
@@ -526,7 +529,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
-    Ring ring;
+    constexpr int BWD_RING_S = BwdRing<VPL>::S;
+    Ring<BWD_RING_S> ring;
     ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
     Row<VPL> av, da_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
@@ -625,10 +629,16 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
     flush_da16<VPL>(da_acc, p.da, d4);
 }
 
-static inline size_t bwd_ring_smem(int d) { return (size_t)RING_WARPS * BWD_RING_S * ((size_t)d * 4 + edge_mask_bytes(d) + 8); }
+static inline int bwd_ring_depth(int d) {
+    const int vpl = (d / 4 + 31) / 32;
+    return vpl <= 2 ? BwdRing<2>::S : (vpl == 3 ? BwdRing<3>::S : BwdRing<4>::S);
+}
+static inline size_t bwd_ring_smem(int d) { return (size_t)RING_WARPS * bwd_ring_depth(d) * ((size_t)d * 4 + edge_mask_bytes(d) + 8); }
 static inline bool use_ring(int d) {
     static const int on = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
-    return on && bwd_ring_smem(d) <= 200 * 1024;      // + 16 KB static for the da_att block reduction
+    const int vpl = (d / 4 + 31) / 32;
+    const size_t static_red = (size_t)RING_WARPS * vpl * 32 * sizeof(float4);      // flush_da16's block reduction buffer
+    return on && bwd_ring_smem(d) + static_red + 1024 <= 227 * 1024;
 }
 
 }  // namespace jmac

@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
 // per SM) instead of by occupancy; the LSU only sees conflict-free LDS.128.  The relation rows S[t], R'[t]
 // are L2-resident: plain loads issued before the wait on the ring.
 // ------------------------------------------------------------------------------------------------
-constexpr int RING_S = 6, RING_ROWS = 2;   // slot = {Q[j], X[j]}; 16 warps x 6 x 2 KB = 192 KB at d = 256
+constexpr int RING_ROWS = 2;               // slot = {Q[j], X[j]}
+// ring depth by row width: 16 warps x 6 x 2 KB = 192 KB at d = 256; wider rows (VPL >= 3, e.g. JMAC_DBPv1's d = 300) get 4 slots
+template <int VPL> struct FwdRing { static constexpr int S = VPL <= 2 ? 6 : 4; };
 
 // one edge of the ring: logit from the shared-memory copies of Q[j] (row 0 of the slot) and the relation row S[t]
 template <int VPL>
@@ -246,6 +248,7 @@ __device__ __forceinline__ int first_item_at_or_after(const Item* items, int n_i
 template <int VPL, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeFwdParams p) {
     extern __shared__ __align__(16) uint8_t ring_raw[];
+    constexpr int RING_S = FwdRing<VPL>::S;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
@@ -483,8 +486,8 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     // which can keep only ~64 KB of gathers in flight per SM -- DESIGN.md section 4); JMAC_EDGE_RING=0 selects the
     // register-staged kernel, which is also the fallback when a ring of d-wide rows does not fit in shared memory.
     static const int use_ring = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
-    const size_t ring_smem = (size_t)RING_WARPS * RING_S * (RING_ROWS * (size_t)d * 4 + 8);
     JMAC_DISPATCH_VPL(d, {
+        const size_t ring_smem = (size_t)RING_WARPS * FwdRing<VPL>::S * (RING_ROWS * (size_t)d * 4 + 8);
         constexpr int U = VPL == 1 ? 4 : 2;
         if (use_ring && plan->E > 0 && ring_smem <= 220 * 1024) {
             // one CTA of RING_WARPS warps per SM

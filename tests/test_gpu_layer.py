@@ -137,6 +137,9 @@ def oracle_run(layer, ei, et, x, r, gout, dtype, training=True, comp_op="sub"):
     (257, 1000, 3, 128, 300),
     (3001, 20001, 41, 256, 1501),     # odd E: the record regions behind the masks start at odd multiples of 8 bytes
     (701, 4999, 9, 300, 333),
+    (600, 4001, 6, 384, 200),         # 3 full float4 per lane: ring kernels with 4 / 7 slots
+    (500, 3001, 5, 400, 100),         # 4 float4 per lane, ragged tail, ring kernels
+    (300, 2000, 4, 512, 0),           # widest rows: the rings do not fit in shared memory, register-staged kernels
     (33, 1, 2, 256, 0),               # a single edge
     (5000, 30001, 40, 256, 2000),     # >= 4096 nodes: the fused attention-input node (tcgen05 GEMMs, epilogue gradient accumulation)
     (4200, 9000, 7, 128, 0),
