@@ -47,7 +47,7 @@ __device__ __forceinline__ float l1_diff(const Row<VPL>& a, const Row<VPL>& b) {
 }
 
 template <int VPL, int U>
-__global__ void __launch_bounds__(256) transe_fwd_kernel(TransEParams p) {
+__global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -59,27 +59,27 @@ __global__ void __launch_bounds__(256) transe_fwd_kernel(TransEParams p) {
         if (live) {
             const float* ent = p.ent[l];
             const float* rel = p.rel[l];
-            int64_t hprev = -1, rprev = -1;
+            int hprev = -1, rprev = -1;                      // ids fit 31 bits (checked by the host): 32-bit keeps the kernel at 3 CTAs / SM
             Row<VPL> hr;
             hr.zero();
             float pos = 0.f;
             for (int kb = 0; kb < p.K1; kb += 32) {
                 const int cnt = min(32, p.K1 - kb);
-                int64_t hv = 0, rv = 0, tv = 0;
+                int hv = 0, rv = 0, tv = 0;
                 if (lane < cnt) {
                     const int64_t m = (int64_t)(kb + lane) * p.B + b;
-                    hv = __ldg(p.h + m); rv = __ldg(p.r + m); tv = __ldg(p.t + m);
+                    hv = (int)__ldg(p.h + m); rv = (int)__ldg(p.r + m); tv = (int)__ldg(p.t + m);
                 }
                 float sc_keep = 0.f;
                 for (int k = 0; k < cnt; k += U) {
                     Row<VPL> tr[U];
-                    int64_t hh[U], rr[U];
+                    int hh[U], rr[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const int kk = min(k + u, cnt - 1);
                         hh[u] = __shfl_sync(FULL, hv, kk);
                         rr[u] = __shfl_sync(FULL, rv, kk);
-                        const int64_t tt = __shfl_sync(FULL, tv, kk);
+                        const int tt = __shfl_sync(FULL, tv, kk);
                         load_row<VPL, true>(tr[u], ent, tt, d4, lane);
                     }
 #pragma unroll
@@ -266,7 +266,7 @@ static int fill_transe(TransEParams& p, const float* const* ent, const float* co
 extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
                                       const int64_t* r, const int64_t* t, int64_t M, int64_t B, int64_t n_ent, int64_t n_rel,
                                       float margin, float* score, float* loss, void* stream) {
-    (void)n_ent; (void)n_rel;
+    JMAC_ARG(n_ent > 0 && n_ent < (int64_t(1) << 31) && n_rel > 0 && n_rel < (int64_t(1) << 31));      // the kernels keep ids in 32 bits
     TransEParams p;
     int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, margin);
     if (rc) return rc;
