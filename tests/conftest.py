@@ -15,6 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "needs_reference: needs /root/reference (build container only)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is a build product (git-ignored): build it once if this checkout does not have it yet."""
+    lib = os.path.join(ROOT, "jmac_b200", "libjmac_b200.so")
+    if not os.path.exists(lib):
+        try:
+            import __graft_entry__
+            __graft_entry__.build()
+        except Exception as ex:        # the tests that need the library then fail with their own message
+            print(f"conftest: could not build libjmac_b200.so: {ex}")
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     has_gpu = torch.cuda.is_available()
