@@ -42,7 +42,11 @@ uint64_t jmac_launch_count(void);
  *   row = edge_index[0] (aggregation target i), col = edge_index[1] (message source j).
  *   n_rel = number of relation rows INCLUDING the self-loop row (= rel_emb.size(0) + 1).
  *   chunk = max edges one warp handles before a segment is split (0 = default 256).
- * Synchronises `stream` (it needs data-dependent sizes).
+ * Synchronises `stream` (it needs data-dependent sizes); the plan is complete on return and may be
+ * used from any stream.  Its arrays come from the device's default stream-ordered memory pool
+ * (cudaMallocAsync; the pool keeps freed blocks, so a rebuilt plan reuses the memory of the
+ * destroyed one).  jmac_plan_destroy waits for the device (any stream may still be reading the
+ * plan) and returns the arrays to that pool.
  * ------------------------------------------------------------------------------------------ */
 typedef struct jmac_plan jmac_plan;
 
