@@ -54,6 +54,24 @@ static cudaError_t dmalloc(T** p, size_t bytes, cudaStream_t st) {
 static void dfree(void* p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
+// Build temporaries of one scope: returned to the pool (stream-ordered) when the scope ends, including on the
+// early-return error paths of JMAC_CUDA / JMAC_LAUNCH_CHECK.
+struct Temps {
+    cudaStream_t st;
+    void* ptrs[12];
+    int n = 0;
+    explicit Temps(cudaStream_t s) : st(s) {}
+    Temps(const Temps&) = delete;
+    Temps& operator=(const Temps&) = delete;
+    ~Temps() { for (int i = 0; i < n; ++i) dfree(ptrs[i], st); }
+    template <typename T>
+    cudaError_t alloc(T** p, size_t bytes) {
+        if (n >= 12) return cudaErrorMemoryAllocation;
+        cudaError_t e = dmalloc(p, bytes, st);
+        if (e == cudaSuccess) ptrs[n++] = *p;
+        return e;
+    }
+};
 
 int plan_scratch(jmac_plan* p, size_t bytes, float** out) {
     if (bytes > p->scratch_bytes) {
@@ -165,8 +183,9 @@ static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cuda
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
     size_t nb = sizeof(int) * (size_t)(nseg + 1);
-    JMAC_CUDA(dmalloc(&n_it, nb, st)); JMAC_CUDA(dmalloc(&n_sl, nb, st)); JMAC_CUDA(dmalloc(&n_sp, nb, st));
-    JMAC_CUDA(dmalloc(&o_it, nb, st)); JMAC_CUDA(dmalloc(&o_sl, nb, st)); JMAC_CUDA(dmalloc(&o_sp, nb, st));
+    Temps tmps(st);
+    JMAC_CUDA(tmps.alloc(&n_it, nb)); JMAC_CUDA(tmps.alloc(&n_sl, nb)); JMAC_CUDA(tmps.alloc(&n_sp, nb));
+    JMAC_CUDA(tmps.alloc(&o_it, nb)); JMAC_CUDA(tmps.alloc(&o_sl, nb)); JMAC_CUDA(tmps.alloc(&o_sp, nb));
     JMAC_CUDA(cudaMemsetAsync(n_it, 0, nb, st)); JMAC_CUDA(cudaMemsetAsync(n_sl, 0, nb, st)); JMAC_CUDA(cudaMemsetAsync(n_sp, 0, nb, st));
     int threads = 256, blocks = (nseg + threads - 1) / threads;
     if (nseg > 0) {
@@ -175,7 +194,7 @@ static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cuda
     }
     // exclusive scans over nseg+1 entries (last entry of the counts is 0) -> totals land at [nseg]
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, n_it, o_it, nseg + 1, st));
-    JMAC_CUDA(dmalloc(&tmp, tmp_bytes, st));
+    JMAC_CUDA(tmps.alloc(&tmp, tmp_bytes));
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_it, o_it, nseg + 1, st));
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_sl, o_sl, nseg + 1, st));
     JMAC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_sp, o_sp, nseg + 1, st));
@@ -191,7 +210,6 @@ static int build_items(const int* ptr, int nseg, int chunk, int keep_empty, cuda
         item_fill_kernel<<<blocks, threads, 0, st>>>(ptr, nseg, chunk, n_it, o_it, o_sl, o_sp, out->items, out->splits);
         JMAC_LAUNCH_CHECK();
     }
-    dfree(n_it, st); dfree(n_sl, st); dfree(n_sp, st); dfree(o_it, st); dfree(o_sl, st); dfree(o_sp, st); dfree(tmp, st);
     return 0;
 }
 
@@ -199,14 +217,14 @@ static int sort_by_int_key(const int* keys_in, int64_t E, int end_bit, cudaStrea
     int* iota = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    JMAC_CUDA(dmalloc(&iota, sizeof(int) * (size_t)(E > 0 ? E : 1), st));
+    Temps tmps(st);
+    JMAC_CUDA(tmps.alloc(&iota, sizeof(int) * (size_t)(E > 0 ? E : 1)));
     int threads = 256;
     int64_t blocks = (E + threads - 1) / threads;
     if (E > 0) { iota_kernel<<<(unsigned)blocks, threads, 0, st>>>(iota, E); JMAC_LAUNCH_CHECK(); }
     JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned*)keys_in, (unsigned*)keys_out, iota, pos_out, (int)E, 0, end_bit, st));
-    JMAC_CUDA(dmalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1, st));
+    JMAC_CUDA(tmps.alloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
     JMAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned*)keys_in, (unsigned*)keys_out, iota, pos_out, (int)E, 0, end_bit, st));
-    dfree(iota, st); dfree(tmp, st);
     return 0;
 }
 
@@ -249,7 +267,8 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
     const unsigned eblocks = (unsigned)((E + threads - 1) / threads);
     const unsigned e1blocks = (unsigned)((E + 1 + threads - 1) / threads);
     int* flags = nullptr;  // [0] = bad index flag, [1] = max degree
-    JMAC_CUDA(dmalloc(&flags, 2 * sizeof(int), st));
+    Temps keep(st);
+    JMAC_CUDA(keep.alloc(&flags, 2 * sizeof(int)));
     JMAC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
 
     // ---- by destination, secondary key relation type
@@ -258,14 +277,15 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         int* v_in = nullptr;
         void* tmp = nullptr;
         size_t tmp_bytes = 0;
-        JMAC_CUDA(dmalloc(&k_in, sizeof(uint64_t) * Eb, st)); JMAC_CUDA(dmalloc(&k_out, sizeof(uint64_t) * Eb, st));
-        JMAC_CUDA(dmalloc(&v_in, sizeof(int) * Eb, st));
+        Temps tmps(st);
+        JMAC_CUDA(tmps.alloc(&k_in, sizeof(uint64_t) * Eb)); JMAC_CUDA(tmps.alloc(&k_out, sizeof(uint64_t) * Eb));
+        JMAC_CUDA(tmps.alloc(&v_in, sizeof(int) * Eb));
         if (E > 0) {
             make_keys_kernel<<<eblocks, threads, 0, st>>>(d_row, d_col, d_type, E, N, NS, R, tb, k_in, v_in, flags);
             JMAC_LAUNCH_CHECK();
         }
         JMAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
-        JMAC_CUDA(dmalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1, st));
+        JMAC_CUDA(tmps.alloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
         JMAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, p->csr_eid, (int)E, 0, tb + nbits, st));
         if (E > 0) {
             fill_csr_kernel<<<eblocks, threads, 0, st>>>(k_out, p->csr_eid, d_col, E, tb, p->csr_src, p->csr_type, p->csr_dst);
@@ -274,9 +294,7 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         int bad = 0;
         JMAC_CUDA(cudaMemcpyAsync(&bad, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         JMAC_CUDA(cudaStreamSynchronize(st));
-        dfree(k_in, st); dfree(k_out, st); dfree(v_in, st); dfree(tmp, st);
         if (bad) {
-            dfree(flags, st);
             set_error("jmac_plan_create: edge_index / edge_type entry out of range (N=%lld, n_rel=%lld)", (long long)N, (long long)R);
             return JMAC_ERANGE;
         }
@@ -292,7 +310,8 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
     // ---- by source (stable: positions stay in destination order inside a source segment)
     {
         int* sorted = nullptr;
-        JMAC_CUDA(dmalloc(&sorted, sizeof(int) * Eb, st));
+        Temps tmps(st);
+        JMAC_CUDA(tmps.alloc(&sorted, sizeof(int) * Eb));
         int rc = sort_by_int_key(p->csr_src, E, sbits, st, sorted, p->csc_pos);
         if (rc) return rc;
         build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)NS, p->colptr);
@@ -304,9 +323,7 @@ static int plan_build(jmac_plan* p, const int64_t* d_row, const int64_t* d_col, 
         build_ptr_kernel<<<e1blocks, threads, 0, st>>>(sorted, E, (int)R, p->typptr);
         JMAC_LAUNCH_CHECK();
         if (E > 0) { gather_int_kernel<<<eblocks, threads, 0, st>>>(p->csr_dst, p->typ_pos, E, p->typ_dst); JMAC_LAUNCH_CHECK(); }
-        dfree(sorted, st);
     }
-    dfree(flags, st);
     int rc = build_items(p->rowptr, (int)N, p->chunk, 1, st, &p->dst_items);
     if (rc) return rc;
     rc = build_items(p->colptr, (int)NS, p->chunk, 1, st, &p->src_items);
