@@ -48,12 +48,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void add_v8(float (&v)[8], const float* p) {
-    float r[8];
+__device__ __forceinline__ void ld_v8(float (&r)[8], const float* p) {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] += r[q];
 }
 __device__ __forceinline__ void st_v8(float* p, const float (&v)[8]) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
@@ -219,17 +216,34 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     tc_ld_wait();
                     if (c + 1 < nchunk) tc_ld32_issue(taddr + (c + 1) * 32, raw[(c + 1) & 1]);
                     if (row < p.M) {
-                        // 256-bit accesses (sm_100): every request of a lane is one full 32-byte sector of its own row
+                        // 256-bit accesses (sm_100): every request of a lane is one full 32-byte sector of its own row.
+                        // Gradient accumulation fused into the epilogue: all addend loads of the chunk are issued before the
+                        // first use (8 requests in flight per thread instead of 2), each thread reads what it overwrites.
+                        float v[4][8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float v[8];
+                        for (int j = 0; j < 4; ++j)
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(raw[c & 1][8 * j + q]);
-                            // gradient accumulation fused into the epilogue (each thread reads the addend chunk it overwrites)
-                            if (d1row) add_v8(v, d1row + c * 32 + 8 * j);
-                            if (d2row) add_v8(v, d2row + c * 32 + 8 * j);
-                            st_v8(crow + c * 32 + 8 * j, v);
+                            for (int q = 0; q < 8; ++q) v[j][q] = __uint_as_float(raw[c & 1][8 * j + q]);
+                        if (d1row) {
+                            float a1[4][8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ld_v8(a1[j], d1row + c * 32 + 8 * j);
+                            if (d2row) {
+                                float a2[4][8];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) ld_v8(a2[j], d2row + c * 32 + 8 * j);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) v[j][q] += a2[j][q];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v[j][q] += a1[j][q];
                         }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) st_v8(crow + c * 32 + 8 * j, v[j]);
                     }
                 }
             }
