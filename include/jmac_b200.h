@@ -46,7 +46,8 @@ uint64_t jmac_launch_count(void);
  * used from any stream.  Its arrays come from the device's default stream-ordered memory pool
  * (cudaMallocAsync; the pool keeps freed blocks, so a rebuilt plan reuses the memory of the
  * destroyed one).  jmac_plan_destroy waits for the device (any stream may still be reading the
- * plan) and returns the arrays to that pool.
+ * plan) and returns the arrays to that pool.  A plan owns the scratch for the partial results of
+ * split segments: edge kernels of ONE plan must not run concurrently on different streams.
  * ------------------------------------------------------------------------------------------ */
 typedef struct jmac_plan jmac_plan;
 
