@@ -343,3 +343,25 @@ def test_completion_loss_multi_equals_separate_calls(golden):
             scale = max(float(want_grad[k].abs().max()), 1e-6)
             atol = 2e-6 if k.endswith("loop_rel") else 1e-7        # loop_rel: mathematically zero in train mode, rounding noise only
             assert float((p.grad - want_grad[k]).abs().max()) <= 1e-4 * scale + atol, k
+
+
+def test_negative_sampler_on_device_feeds_the_scorer():
+    """jmac_b200.sampling on CUDA tensors: valid, distinct negatives in the layout completion_loss expects (train.py:347-352)."""
+    from jmac_b200 import functional as JF
+    from jmac_b200.sampling import TripleIndex, sample_negatives
+    rng = np.random.default_rng(5)
+    n_ent, n_rel, B, K, d = 3000, 11, 512, 25, 64
+    tri = np.stack([rng.integers(0, n_ent, 20000), rng.integers(0, n_rel, 20000), rng.integers(0, n_ent, 20000)], 1)
+    idx = TripleIndex(tri, n_ent, n_rel, device="cuda")
+    batch = torch.from_numpy(tri[:B]).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    neg = sample_negatives(idx, batch[:, 0], batch[:, 1], K, generator=g)
+    assert neg.is_cuda and neg.shape == (B, K)
+    assert not bool(idx.contains(batch[:, :1], batch[:, 1:2], neg).any())
+    assert bool((torch.sort(neg, 1)[0][:, 1:] != torch.sort(neg, 1)[0][:, :-1]).all())
+    ents = [torch.randn(n_ent, d, device="cuda", requires_grad=True)]
+    rels = [torch.randn(n_rel, d, device="cuda", requires_grad=True)]
+    loss = JF.transe_margin_loss(ents, rels, batch[:, 0].repeat(K + 1), batch[:, 1].repeat(K + 1),
+                                 torch.cat((batch[:, 2], neg.t().reshape(-1))), B, 5.0)      # negatives [K, B] flattened: position B + k*B + b
+    loss.sum().backward()
+    assert torch.isfinite(loss).all() and ents[0].grad is not None
