@@ -1,4 +1,4 @@
-"""Multi-GPU (NCCL) parity: the destination-sharded encoder on 2 GPUs against the single-GPU CUDA
+"""Multi-GPU (NCCL) parity: the destination-sharded encoder and the row-sharded alignment evaluation on 2 GPUs against the single-GPU CUDA
 path on the same inputs.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box."""
 import os
 import socket
@@ -73,3 +73,29 @@ def _worker(rank, world, port, N, E, R, d):
                                  (12000, 100001)])       # shards of ~6000 rows: the fused attention-input node on a gathered source table
 def test_sharded_encoder_matches_single_gpu_nccl(N, E):
     mp.spawn(_worker, args=(2, _free_port(), N, E, 30, 256), nprocs=2, join=True)
+
+
+def _align_worker(rank, world, port, n1, n2, d, csls):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from jmac_b200 import finding as F
+        g = torch.Generator(device=dev).manual_seed(3)
+        n = min(n1, n2)
+        e1 = torch.nn.functional.normalize(torch.randn(n1, d, device=dev, generator=g))
+        e2 = torch.nn.functional.normalize(torch.randn(n2, d, device=dev, generator=g))
+        e2[:n] = torch.nn.functional.normalize(e1[:n] + 1.5 * torch.nn.functional.normalize(torch.randn(n, d, device=dev, generator=g)))
+        A, B = F.to_bf16_rows(e1[:n]), F.to_bf16_rows(e2)            # gold column of row i = i
+        ranks1, top1 = F.alignment_ranks_bf16(A, B, csls_k=csls)                       # this rank alone
+        ranks2, top2 = F.alignment_ranks_bf16(A, B, csls_k=csls, group=dist.group.WORLD)  # rows sharded over the ranks
+        assert torch.equal(ranks1, ranks2) and torch.equal(top1, top2)                  # same kernels on disjoint rows: bit-identical
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("n1,n2,csls", [(3000, 3000, 10), (1025, 2500, 0)])
+def test_row_sharded_alignment_matches_single_gpu_nccl(n1, n2, csls):
+    mp.spawn(_align_worker, args=(2, _free_port(), n1, n2, 256, csls), nprocs=2, join=True)
