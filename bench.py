@@ -188,6 +188,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     sections = set(ALL_SECTIONS if args.sections == "all" else [s for s in args.sections.split(",") if s])
+    args.warmup = max(args.warmup, 3)                    # timing rule: at least 3 untimed warm-up steps; the line reports what was run
+    args.steps = max(args.steps, 1)
     lib = _lib.load()
     cfg = workload_config(world, args.scale)
     N, R, E, B, K, NA = cfg["entities"], cfg["relations"], cfg["edges"], cfg["scorer_batch"], cfg["negatives"], cfg["align_rows"]
