@@ -13,7 +13,8 @@ gradient tolerances).
 
 Parity pinning: the reference ships no tests and no golden vectors.  The
 oracle is pinned against outputs of the reference itself, imported unmodified in the build
-container by ``oracle/gen_golden.py`` (fixtures in ``tests/golden/*.npz``); see
+container by ``oracle/gen_golden.py`` (synthetic cases) and ``oracle/gen_golden_dbp5l.py`` (a trace on the
+el/en graphs of the in-repo DBP-5L data), fixtures in ``tests/golden/*.npz``; see
 ``tests/test_oracle_golden.py``.
 
 Third-party arithmetic restated here (absent from /root/reference): ``torch_scatter``
