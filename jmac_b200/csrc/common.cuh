@@ -54,6 +54,7 @@ struct jmac_plan {
     int64_t E = 0, N = 0, N_src = 0, n_rel = 0;   // N = destination (aggregation) nodes, N_src = source table rows
     int chunk = 256;
     int max_deg = 0;
+    int device = 0;                               // the device the plan's arrays live on (restored around destroy)
     // by destination (CSR)
     int *rowptr = nullptr, *csr_src = nullptr, *csr_type = nullptr, *csr_eid = nullptr, *csr_dst = nullptr;
     float* sqrt_deg = nullptr;

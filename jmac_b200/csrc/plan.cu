@@ -240,12 +240,16 @@ extern "C" int jmac_plan_destroy(jmac_plan* p) {
     if (!p) return 0;
     // One device-wide wait (any stream may still be reading the plan), then stream-ordered frees back into the pool:
     // the ~20 cudaFree calls this replaces each synchronised the device and returned the memory to the OS.
+    int cur = p->device;
+    cudaGetDevice(&cur);
+    if (cur != p->device) cudaSetDevice(p->device);      // a process that drives several devices may destroy the plan from another one
     cudaDeviceSynchronize();
     void* ptrs[] = {p->rowptr, p->csr_src, p->csr_type, p->csr_eid, p->csr_dst, p->sqrt_deg, p->colptr, p->csc_pos, p->csc_dst, p->typptr,
                     p->typ_pos, p->typ_dst, p->dst_items.items, p->dst_items.splits, p->src_items.items, p->src_items.splits,
                     p->typ_items.items, p->typ_items.splits};
     for (void* q : ptrs) dfree(q, 0);
     if (p->scratch) cudaFree(p->scratch);
+    if (cur != p->device) cudaSetDevice(cur);
     delete p;
     return 0;
 }
@@ -347,6 +351,7 @@ extern "C" int jmac_plan_create_bipartite(const int64_t* d_row, const int64_t* d
     if (!p) return JMAC_ENOMEM;
     p->E = E; p->N = N_dst; p->N_src = N_src; p->n_rel = n_rel;
     p->chunk = chunk > 0 ? chunk : 256;
+    if (cudaGetDevice(&p->device) != cudaSuccess) p->device = 0;
     int rc = plan_build(p, d_row, d_col, d_type, (cudaStream_t)stream);
     if (rc == 0 && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = JMAC_EINVAL;   // complete on return: usable from any stream
     if (rc) { jmac_plan_destroy(p); return rc; }
