@@ -11,6 +11,13 @@ graph; value = layer-edges per second = (2 * E) / step time, whole job.  With N 
 is destination-sharded over the ranks (strong scaling; halo all-gather / reduce-scatter over NCCL).
 
 Further sections on the same JSON line (each timed separately, after the headline region):
+  c2           the reference's real training step (BASELINE.json configs[1] sizes): JMAC.completion_loss
+               fwd+bwd+Adam on a DBP-5L-shaped pair of graphs (en/fr sizes, B=1000, K=25, d=256), host-fed
+               batches and loss read-back like train.py:328-364, with the oracle's un-factored algorithm in
+               PyTorch eager ON THE SAME GPU beside it (the kernel-level bar)
+  c3           alignment at the reference's sizes (configs[2]): evaluation.test (cosine + CSLS(10) + Hits@k) at
+               2,617^2 and 10,500^2, get_neg 4,500 x 30,000 (k=25), compute_alignment_quality 15k x 15k; same
+               eager-GPU comparison
   roofline     every edge kernel timed alone with CUDA events vs MEASURED_PEAKS.json (N=1)
   scorer       completion scorer fwd+bwd, B=65536 positives x K=64 negatives, 2 layers (N=1)
   align        alignment scorer: 1M x 1M x 256 bf16 similarity + CSLS(10) + Hits@k, row-sharded over
@@ -35,7 +42,10 @@ sys.path.insert(0, ROOT)
 D = 256
 FULL = dict(N=2_000_000, R=2_000, E=40_000_000, B=65_536, K=64, ALIGN=1_048_576)
 CPU_SAMPLE = dict(N=50_000, R=2_000, E=1_000_000)      # same mean degree (20) and width as C4
-ALL_SECTIONS = ("roofline", "scorer", "linkpred", "align", "e2e", "cpu")
+ALL_SECTIONS = ("roofline", "scorer", "linkpred", "align", "c2", "c3", "e2e", "cpu")
+# DBP-5L en / fr shapes: entities, GNN edges, max in-degree; 960 relations (+1 loop row) per KG,
+# 56,589 entities and 4,805 relation rows in the joint tables; batch 1000 x 25 negatives; ~2.6k seed links
+C2 = dict(N1=13_996, E1=72_703, N2=13_176, E2=44_844, MAXDEG=2_769, R=961, NUM_ENT=56_589, NUM_REL=4_805, B=1_000, K=25, LINKS=2_617)
 
 
 def peaks():
@@ -132,6 +142,214 @@ def cpu_layer_step(N, R, E, steps, warmup, seed=0):
     return E / dt, dt, torch.get_num_threads()
 
 
+def zipf_destinations(N, E, cap, gen, dev, a=1.1):
+    """E destination ids with a power-law in-degree: rank k drawn from p(k) ~ k^-a over a random permutation of the
+    N entities (inverse-CDF sampling), in-degree capped at ``cap`` (overflow re-drawn uniformly) -- SURVEY 8d."""
+    import torch
+    u = torch.rand(E, device=dev, generator=gen, dtype=torch.float64)
+    k = ((u * (float(N) ** (1 - a) - 1.0) + 1.0) ** (1.0 / (1 - a))).floor().clamp_(1, N).to(torch.int64) - 1
+    cnt = torch.bincount(k, minlength=N)
+    over = cnt > cap
+    if bool(over.any()):
+        pos_in_node = torch.argsort(torch.argsort(k, stable=True), stable=True) - (torch.cumsum(cnt, 0) - cnt)[k]
+        redo = over[k] & (pos_in_node >= cap)
+        k[redo] = torch.randint(0, N, (int(redo.sum()),), device=dev, generator=gen)
+    perm = torch.randperm(N, device=dev, generator=gen)
+    return perm[k]
+
+
+def planted_pair(n, d, noise, gen, dev):
+    """Unit-norm Gaussian rows with planted matches e2 = normalize(e1 + noise * unit noise)."""
+    import torch
+    F = torch.nn.functional
+    e1 = F.normalize(torch.randn(n, d, device=dev, generator=gen))
+    e2 = F.normalize(e1 + noise * F.normalize(torch.randn(n, d, device=dev, generator=gen)))
+    return e1, e2
+
+
+def wall_time(fn, warmup, iters):
+    """Host wall clock around a host-facing API call (inputs on the host, result on the host), device drained on
+    both sides.  ms per call."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / iters * 1e3
+
+
+def section_c2(dev, rank, lib, graphed=True):
+    """BASELINE.json configs[1] sizes: one JMAC.completion_loss training step (both encoders fwd+bwd, TransE margin scorer
+    on (1+K)*B triples x 2 layers, seed-link alignment term, Adam) on a DBP-5L-shaped pair of graphs, fed like
+    train.py:328-364 (host batch -> device, loss.item() read back).  Same step by the oracle's un-factored algorithm
+    (materialised [E,d] gathers, [E,2d] concat GEMM, scatter-softmax, index_add) in PyTorch eager on this GPU."""
+    import numpy as np
+    import torch
+    from types import SimpleNamespace
+    from jmac_b200 import JMAC
+    from oracle import jmac_oracle as O          # the eager-GPU comparator only; never on the product path
+    c = C2
+    gen = torch.Generator(device=dev).manual_seed(2)
+    B, K = c["B"], c["K"]
+    args = SimpleNamespace(dim=D, device=dev, dropout=0.0, leaky_relu_w=0.05, comp_op="sub", margin_align=1.0, num_negative=K,
+                           margin_completion=5.0, num_gcn_layer=2, no_name_info=True, batch_size=B)
+    torch.manual_seed(0)
+    model = JMAC(args, np.zeros((c["NUM_ENT"], 300), dtype=np.float32), c["NUM_REL"], c["NUM_ENT"]).to(dev)
+    model.train()
+
+    def graph(N, E):
+        row = zipf_destinations(N, E, c["MAXDEG"], gen, dev)
+        col = torch.randint(0, N, (E,), device=dev, generator=gen)
+        return torch.stack([row, col]), torch.randint(0, c["R"] - 1, (E,), device=dev, generator=gen)
+    ei1, et1 = graph(c["N1"], c["E1"])
+    ei2, et2 = graph(c["N2"], c["E2"])
+    links = torch.stack([torch.randperm(c["N1"], device=dev, generator=gen)[:c["LINKS"]],
+                         torch.randperm(c["N2"], device=dev, generator=gen)[:c["LINKS"]]], 1).cpu().numpy()
+    feed = {"links": links, "ent_bases1": [0, c["N1"]], "rel_bases1": [0, c["R"]],
+            "ent_bases2": [c["N1"], c["N1"] + c["N2"]], "rel_bases2": [c["R"], 2 * c["R"]]}
+    rng = np.random.default_rng(7)
+    n_batches = 8                                   # distinct host batches, cycled (train.py's DataLoader yields a new one per step)
+    host = []
+    for _ in range(n_batches):
+        sub, rel, obj = rng.integers(0, c["N1"], B), rng.integers(0, c["R"] - 1, B), rng.integers(0, c["N1"], B)
+        neg = rng.integers(0, c["N1"], (B, K))
+        host.append((torch.from_numpy(np.stack([sub, rel, obj], 1)).pin_memory(), torch.from_numpy(neg).pin_memory()))
+
+    def make_data(i):
+        tri, neg = host[i % n_batches]
+        tri = tri.to(dev, non_blocking=True)                                         # train.py:343
+        sub, rel, obj = tri[:, 0], tri[:, 1], tri[:, 2]
+        neg = neg.to(dev, non_blocking=True).view(-1)                                # train.py:349-350
+        return {"batch_h": sub.repeat(K + 1), "batch_r": rel.repeat(K + 1), "batch_t": torch.cat((obj, neg))}
+
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    it = [0]
+
+    def step():
+        opt.zero_grad()
+        loss = model.completion_loss(make_data(it[0]), ei1, et1, ei2, et2, feed, True)
+        loss.backward()
+        opt.step()
+        it[0] += 1
+        return float(loss.item())                                                    # train.py:357
+    first_loss = step()
+    n0 = lib.jmac_launch_count()
+    ms = wall_time(step, 5, 30)
+    launches = (lib.jmac_launch_count() - n0) / 35.0
+    triples = (K + 1) * B
+    out = {"metric": "completion_steps_per_s", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "scored_triples_per_s": triples * 2 / (ms * 1e-3),
+           "layer_edges_per_s": (c["E1"] + c["E2"]) / (ms * 1e-3), "jmac_kernel_launches_per_step": launches,
+           "workload": f"DBP-5L-shaped en/fr pair (synthetic, Zipf(1.1) in-degree capped at {c['MAXDEG']}): {c['N1']}+{c['N2']} entities, "
+                       f"{c['E1']}+{c['E2']} edges, {c['R']} relation rows per KG, d={D}, B={B}, K={K}, {c['LINKS']} seed links; "
+                       "JMAC.completion_loss + backward + Adam, host-fed batch, loss.item()",
+           "timing": "host wall clock per step (device drained on both sides), 30 steps after 5 warm-up"}
+    # ---- same step, oracle algorithm in PyTorch eager on this GPU (identical initial state, identical batches)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    train_keys = [k for k, p_ in model.named_parameters() if p_.requires_grad]
+    for k in train_keys:
+        sd[k].requires_grad_(True)
+    opt_e = torch.optim.Adam([sd[k] for k in train_keys], lr=3e-4)
+    it[0] = 0
+
+    def eager_step():
+        opt_e.zero_grad()
+        loss = O.completion_loss(sd, make_data(it[0]), ei1, et1, ei2, et2, feed, True, batch_size=B, margin=5.0)
+        loss.backward()
+        opt_e.step()
+        it[0] += 1
+        return float(loss.item())
+    first_eager = eager_step()
+    ms_e = wall_time(eager_step, 3, 10)
+    out["eager_gpu"] = {"ms_per_step": ms_e, "steps_per_s": 1e3 / ms_e, "what": "oracle (reference algorithm, un-factored) in PyTorch eager on the same B200"}
+    out["speedup_vs_eager_gpu"] = ms_e / ms
+    out["first_step_loss"] = {"jmac_b200": first_loss, "eager": first_eager, "rel_diff": abs(first_loss - first_eager) / abs(first_eager)}
+    if graphed:
+        try:
+            from jmac_b200.graphs import GraphedCompletionStep
+            model.load_state_dict(sd0)
+            gopt = torch.optim.Adam(model.parameters(), lr=3e-4, capturable=True)
+            gstep = GraphedCompletionStep(model, gopt, ei1, et1, ei2, et2, feed, True, batch_rows=(K + 1) * B)
+            it[0] = 0
+
+            def graphed():
+                d_ = make_data(it[0])
+                it[0] += 1
+                return float(gstep(d_).item())
+            g_first = graphed()
+            ms_g = wall_time(graphed, 5, 30)
+            out["cuda_graph"] = {"ms_per_step": ms_g, "steps_per_s": 1e3 / ms_g, "first_step_loss": g_first,
+                                 "what": "the same step captured once in a CUDA graph (jmac_b200.graphs.GraphedCompletionStep) and replayed"}
+            out["speedup_graph_vs_eager_gpu"] = ms_e / ms_g
+        except Exception as ex:            # the un-graphed numbers above stand on their own
+            out["cuda_graph"] = {"error": repr(ex)[:300]}
+    return out
+
+
+def section_c3(dev, rank, lib):
+    """BASELINE.json configs[2] sizes: the alignment scorer as the reference calls it (numpy / CPU-tensor inputs, python
+    floats out) next to the same algorithm as dense PyTorch eager ops on this GPU (float64 cosine, topk CSLS, full argsort)."""
+    import numpy as np
+    import torch
+    from jmac_b200 import finding as JFind
+    from oracle import jmac_oracle as O
+    gen = torch.Generator(device=dev).manual_seed(3)
+    out = {"workload": "planted-match unit-norm embeddings, d=256; evaluation.test(metric='cosine', csls_k=10, accurate=True) rows/s = n / time"}
+    for n in (2_617, 10_500):
+        e1, e2 = planted_pair(n, D, 1.5, gen, dev)
+        h1, h2 = e1.cpu().numpy(), e2.cpu().numpy()
+        res = {}
+
+        def ours():
+            res["o"] = JFind.test(h1, h2, None, [1, 5, 10], 8, metric="cosine", normalize=False, csls_k=10, accurate=True)
+
+        def eager():
+            res["e"] = O.greedy_alignment_torch(torch.from_numpy(h1).to(dev), torch.from_numpy(h2).to(dev), (1, 5, 10), 10)
+        ms, ms_e = wall_time(ours, 2, 5), wall_time(eager, 1, 3)
+        _, hits, mr, mrr = res["o"]
+        eh, emr, emrr, _ = res["e"]
+        out[f"test_{n}"] = {"rows_per_s": n / (ms * 1e-3), "ms": ms, "eager_gpu_ms": ms_e, "speedup_vs_eager_gpu": ms_e / ms,
+                            "hits": [float(x) for x in hits], "mr": mr, "mrr": mrr, "eager_hits": [round(x, 3) for x in eh], "eager_mr": emr,
+                            "eager_mrr": emrr, "sim_grid_ctas": int(lib.jmac_sim_grid(n, n, 1)), "sms": int(lib.jmac_sm_count())}
+    # hard-negative mining: get_neg(ILL[4500], emb_src[15000], emb_dst[30000], 25)
+    src = torch.nn.functional.normalize(torch.randn(15_000, D, device=dev, generator=gen))
+    dst = torch.nn.functional.normalize(torch.randn(30_000, D, device=dev, generator=gen))
+    ill = torch.randperm(15_000, device=dev, generator=gen)[:4_500].cpu().tolist()
+    src_c, dst_c = src.cpu(), dst.cpu()                            # the reference feeds CPU tensors (get_emb(pyt=True))
+    res = {}
+
+    def ours_neg():
+        res["o"] = JFind.get_neg(ill, src_c, dst_c, 25)
+
+    def eager_neg():
+        res["e"] = O.get_neg(ill, src_c.to(dev), dst_c.to(dev), 25).cpu()
+    ms, ms_e = wall_time(ours_neg, 2, 5), wall_time(eager_neg, 1, 3)
+    same = float((res["o"].view(-1, 25).sort(1)[0] == res["e"].view(-1, 25).sort(1)[0]).all(1).float().mean())
+    out["get_neg_4500x30000_k25"] = {"ms": ms, "rows_per_s": 4_500 / (ms * 1e-3), "eager_gpu_ms": ms_e, "speedup_vs_eager_gpu": ms_e / ms,
+                                     "rows_with_identical_index_set": same}
+    # alignment quality / seed enlargement: compute_alignment_quality on two 15k KGs with 10.5k candidate entities each
+    e1, e2 = planted_pair(15_000, D, 1.5, gen, dev)
+    l1 = torch.randperm(15_000, device=dev, generator=gen)[:10_500].cpu().tolist()
+    l2 = torch.randperm(15_000, device=dev, generator=gen)[:10_500].cpu().tolist()
+    e1c, e2c = e1.cpu(), e2.cpu()
+
+    def ours_q():
+        ent, s1, s2 = JFind.compute_alignment_quality(e1c, e2c, l1, l2)
+        res["oq"] = (float(ent), s1.max(dim=1)[0])
+
+    def eager_q():
+        ent, s1, s2 = O.compute_alignment_quality(e1c.to(dev), e2c.to(dev), l1, l2)
+        res["eq"] = (float(ent), s1.max(dim=1)[0].cpu())
+    ms, ms_e = wall_time(ours_q, 1, 3), wall_time(eager_q, 1, 2)
+    out["alignment_quality_15k"] = {"ms": ms, "eager_gpu_ms": ms_e, "speedup_vs_eager_gpu": ms_e / ms, "entropy": res["oq"][0],
+                                    "eager_entropy": res["eq"][0],
+                                    "rowmax_max_rel_diff": float(((res["oq"][1] - res["eq"][1]).abs() / res["eq"][1]).max())}
+    return out
+
+
 def workload_config(n_gpus, scale=1.0):
     w = {k: (int(v * scale) if k in ("N", "E", "B", "ALIGN") else v) for k, v in FULL.items()}
     w["ALIGN"] = max(256, w["ALIGN"] // 256 * 256)
@@ -206,23 +424,10 @@ def run_b200(args):
     ei = torch.randint(0, N, (2, E), device=dev, generator=gen)
     et = torch.randint(0, R, (E,), device=dev, generator=gen)
     if args.graph == "zipf":
-        # power-law in-degree: destination = rank drawn from Zipf(1.1) over a random permutation of the entities,
-        # capped at 1e5 in-edges per entity (SURVEY 8d, C4 variant).  Inverse-CDF sampling of p(k) ~ k^-1.1, k in [1, N].
-        a = 1.1
-        u = torch.rand(E, device=dev, generator=gen, dtype=torch.float64)
-        k = ((u * (float(N) ** (1 - a) - 1.0) + 1.0) ** (1.0 / (1 - a))).floor().clamp_(1, N).to(torch.int64) - 1
-        cnt = torch.bincount(k, minlength=N)
-        over = cnt > 100_000
-        if bool(over.any()):                               # re-draw the overflow of capped hubs uniformly
-            pos_in_node = torch.argsort(torch.argsort(k, stable=True), stable=True) - (torch.cumsum(cnt, 0) - cnt)[k]
-            redo = over[k] & (pos_in_node >= 100_000)
-            k[redo] = torch.randint(0, N, (int(redo.sum()),), device=dev, generator=gen)
-            del pos_in_node, redo
-        perm = torch.randperm(N, device=dev, generator=gen)
-        ei[0] = perm[k]
+        # power-law in-degree (the primary C4 variant): Zipf(1.1) over a random permutation, hubs capped at 1e5 in-edges
+        ei[0] = zipf_destinations(N, E, 100_000, gen, dev)
         cfg["workload"] = cfg["workload"].replace("(uniform)", "(Zipf(1.1) in-degree capped at 1e5)")
         cfg["max_in_degree"] = int(torch.bincount(ei[0], minlength=N).max())
-        del u, k, cnt, over, perm
     x0 = (torch.randn(N, D, device=dev, generator=gen) * 0.1).requires_grad_(True)
     rel = (torch.randn(R, D, device=dev, generator=gen) * 0.1).requires_grad_(True)
     gout = torch.randn(N, D, device=dev, generator=gen)
@@ -419,6 +624,11 @@ def run_b200(args):
                          "hits@1": float((ranks < 1).mean()), "hits@10": float((ranks < 10).mean()), "mrr": float((1.0 / (ranks + 1)).mean())}
         del A, Bm
 
+    if single and "c2" in sections:
+        line["c2"] = section_c2(dev, rank, lib)
+    if single and "c3" in sections:
+        line["c3"] = section_c3(dev, rank, lib)
+
     if "e2e" in sections:
         # ---- e2e: HOST inputs every step (pinned), graph plan rebuilt, result read back.  N>1: every rank uploads its
         # own rows of X and its own edge shard (a deployment keeps the partitions on the hosts), the first layer
@@ -539,7 +749,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N/E/B for debugging (bench numbers need 1.0)")
-    ap.add_argument("--graph", default="uniform", choices=["uniform", "zipf"], help="C4 in-degree distribution")
+    ap.add_argument("--graph", default="zipf", choices=["uniform", "zipf"], help="C4 in-degree distribution (zipf = the primary variant of SURVEY 8d)")
     ap.add_argument("--sections", default="all", help="comma list of: " + ",".join(ALL_SECTIONS) + " (or 'all', or '' for headline only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -211,21 +211,45 @@ int jmac_l1_rank(const float* const* ent, const float* const* rel, int n_layers,
  *  modules/finding/alignment.py:87-112 calculate_rank, modules/utils/util.py:31-54 get_neg).
  * The n1 x n2 matrix is never materialised.
  * ------------------------------------------------------------------------------------------ */
+/* Two operand precisions.
+ *   bf16 (jmac_sim_topk, jmac_sim_softmax_stats): rows rounded to bf16, one kind::f16 MMA per K step; the mode for
+ *     the 1M x 1M problem of BASELINE.json configs[4].  dpad multiple of 64, <= 320.
+ *   fp32-accurate 3xTF32 (the *_f32 entry points): every table is passed as two fp32 tables hi + lo produced by
+ *     jmac_to_tf32_rows; three kind::tf32 MMAs per K step; |S - exact| ~ 1e-6 sum|a||b|, i.e. fp32-GEMM accuracy.  This is
+ *     what the reference computes (f64 cdist -> f32, similarity.py:44-46; fp32 mm, util.py:52; train.py:239-257) and the
+ *     default of the Python host for test / valid / get_neg / compute_alignment_quality.  dpad multiple of 32, <= 4096.
+ * Small problems (< 4 row blocks of 256 per SM) are cut into one equal run of 256x128 tiles per SM so that the sizes the
+ * reference evaluates (2.6k-30k rows) use every SM; the per-piece partial results live in `workspace`
+ * (jmac_sim_workspace_bytes; 16-byte aligned; NULL or too small = unsplit launch, at most one CTA per 256 rows) and
+ * are merged in ascending column order: top-k, counts and the gold entry are bit-identical to the unsplit sweep. */
+int jmac_sm_count(void);
+size_t jmac_sim_workspace_bytes(int64_t n1, int64_t n2, int k);
+/* CTAs the similarity kernel launches for an n1 x n2 problem with (split != 0) / without a workspace. */
+int jmac_sim_grid(int64_t n1, int64_t n2, int split);
+
 /* fp32 rows src[idx[r]] (idx NULL = identity), optionally L2-normalised (cosine metric), rounded to
  * bf16 and zero-padded to dpad (multiple of 64) columns: dst[n_rows, dpad]. */
 int jmac_to_bf16_rows(const float* src, int d, const int64_t* idx, int64_t n_rows, int normalize,
                       uint16_t* dst, int dpad, void* stream);
-/* S = A . B^T (bf16 inputs [n1,dpad], [n2,dpad], fp32 accumulation); per row i of A, over all j:
+/* Same gather / normalisation (norm accumulated in fp64), split for the 3xTF32 product:
+ * hi = RN-to-TF32(v), lo = RN-to-TF32(v - hi), both [n_rows, dpad] fp32, dpad a multiple of 32. */
+int jmac_to_tf32_rows(const float* src, int d, const int64_t* idx, int64_t n_rows, int normalize,
+                      float* hi, float* lo, int dpad, void* stream);
+/* S = A . B^T (inputs [n1,dpad], [n2,dpad], fp32 accumulation); per row i of A, over all j:
  *   v_ij = (alpha * S_ij - r1[i]) - r2[j]            (r1, r2 may be NULL = 0; r2 must be readable up to
  *                                                      the next multiple of 128 entries, 16-byte aligned)
  *   topv/topi[n1,k] : the k largest v_ij, descending, ties -> lower j     (k = 0: skipped, k <= 32)
  *   gold_cnt[i]     : #{ j : v_ij > gold_val[i] }                          (NULL: skipped)
- *   diag[i]         : raw S at column gold_col[i]                           (NULL: skipped)
- * dpad <= 256. */
+ *   diag[i]         : raw S at column gold_col[i]                           (NULL: skipped) */
 int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, int dpad, int k,
                   float alpha, const float* r1, const float* r2, const int32_t* gold_col,
                   const float* gold_val, int32_t* gold_cnt, float* diag, float* topv,
-                  int32_t* topi, void* stream);
+                  int32_t* topi, void* workspace, size_t workspace_bytes, void* stream);
+int jmac_sim_topk_f32(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
+                      int64_t n1, int64_t n2, int dpad, int k, float alpha, const float* r1,
+                      const float* r2, const int32_t* gold_col, const float* gold_val,
+                      int32_t* gold_cnt, float* diag, float* topv, int32_t* topi, void* workspace,
+                      size_t workspace_bytes, void* stream);
 /* Softmax statistics of x_ij = alpha * S_ij per row i, never materialising the matrix
  * (compute_alignment_quality, train.py:231-259: softmax(simi * 20), its entropy, its row max/argmax).
  * Rows with row_mask[i] != 0 and columns with col_mask[j] != 0 take x = masked_value instead
@@ -236,7 +260,12 @@ int jmac_sim_topk(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, 
 int jmac_sim_softmax_stats(const uint16_t* A, const uint16_t* B, int64_t n1, int64_t n2, int dpad,
                            float alpha, const float* row_mask, const float* col_mask,
                            float masked_value, float* out_max, int32_t* out_arg, float* out_Z,
-                           float* out_W, void* stream);
+                           float* out_W, void* workspace, size_t workspace_bytes, void* stream);
+int jmac_sim_softmax_stats_f32(const float* A_hi, const float* A_lo, const float* B_hi,
+                               const float* B_lo, int64_t n1, int64_t n2, int dpad, float alpha,
+                               const float* row_mask, const float* col_mask, float masked_value,
+                               float* out_max, int32_t* out_arg, float* out_Z, float* out_W,
+                               void* workspace, size_t workspace_bytes, void* stream);
 /* out[i] = (alpha * diag[i] - r1[i]) - r2[gold_col[i]], with the exact operation order of the
  * epilogue above, so that the gold entry never counts as greater than itself. */
 int jmac_csls_gold(float alpha, const float* diag, const float* r1, const float* r2,

@@ -42,10 +42,16 @@ _SIGNATURES = {
     "jmac_pair_cos_fwd": (c_int, [P, P, c_int, P, P, c_int64, P, P]),
     "jmac_pair_cos_bwd": (c_int, [P, P, c_int, P, P, c_int64, P, P, P, P]),
     "jmac_l1_dist": (c_int, [P, P, c_int, c_int, P, P, c_int64, c_int64, c_int, P, P]),
+    "jmac_sm_count": (c_int, []),
+    "jmac_sim_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "jmac_sim_grid": (c_int, [c_int64, c_int64, c_int]),
     "jmac_to_bf16_rows": (c_int, [P, c_int, P, c_int64, c_int, P, c_int, P]),
-    "jmac_sim_topk": (c_int, [P, P, c_int64, c_int64, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P]),
+    "jmac_to_tf32_rows": (c_int, [P, c_int, P, c_int64, c_int, P, P, c_int, P]),
+    "jmac_sim_topk": (c_int, [P, P, c_int64, c_int64, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "jmac_sim_topk_f32": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "jmac_csls_gold": (c_int, [c_float, P, P, P, P, c_int64, P, P]),
-    "jmac_sim_softmax_stats": (c_int, [P, P, c_int64, c_int64, c_int, c_float, P, P, c_float, P, P, P, P, P]),
+    "jmac_sim_softmax_stats": (c_int, [P, P, c_int64, c_int64, c_int, c_float, P, P, c_float, P, P, P, P, P, c_size_t, P]),
+    "jmac_sim_softmax_stats_f32": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_float, P, P, c_float, P, P, P, P, P, c_size_t, P]),
     "jmac_l1_rank": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int, P, P, P, P]),
 }
 

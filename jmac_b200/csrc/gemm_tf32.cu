@@ -93,6 +93,7 @@ struct GemmParams {
     int ldc;
     const float *D1, *D2;   // optional [M,N] addends of the epilogue (C = A.B^T + D1 + D2), leading dimension ldd; may alias C
     int ldd;
+    int exact_lo;           // != 0: the lo terms are rounded to TF32 (nothing left for the tensor core to truncate) and lo.lo is added
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -165,6 +166,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             tc_mma_tf32(d_tmem, ahi + o, bhi + o, idesc, (kb | kk) != 0 ? 1u : 0u);
                             tc_mma_tf32(d_tmem, alo + o, bhi + o, idesc, 1u);
                             tc_mma_tf32(d_tmem, ahi + o, blo + o, idesc, 1u);
+                            if (p.exact_lo & 2) tc_mma_tf32(d_tmem, alo + o, blo + o, idesc, 1u);
                         }
                     }
                     tc_commit(empty0 + 8 * s);
@@ -192,6 +194,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     h.y = tf32_rna(x.y); l.y = x.y - h.y;
                     h.z = tf32_rna(x.z); l.z = x.z - h.z;
                     h.w = tf32_rna(x.w); l.w = x.w - h.w;
+                    if (p.exact_lo & 1) { l.x = tf32_rna(l.x); l.y = tf32_rna(l.y); l.z = tf32_rna(l.z); l.w = tf32_rna(l.w); }
                     hi[i] = h;
                     lo[i] = l;
                 }
@@ -521,6 +524,8 @@ extern "C" int jmac_gemm_tf32x3_add(const float* A, int64_t lda, const float* B_
     GemmParams p;
     p.M = (int)M; p.N = N; p.nkb = K / G_BK; p.C = C; p.ldc = (int)ldc;
     p.D1 = D1; p.D2 = D2; p.ldd = (int)ldd;
+    static const int gemm_mode = getenv("JMAC_GEMM_MODE") ? atoi(getenv("JMAC_GEMM_MODE")) : 0;
+    p.exact_lo = gemm_mode;
     const int n_mb = (int)((M + G_BM - 1) / G_BM);
     const int grid = n_mb < sm_count() ? n_mb : sm_count();
     JMAC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));

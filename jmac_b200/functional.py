@@ -97,6 +97,8 @@ class GraphPlan:
 
 _PLAN_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _PLAN_CACHE_SIZE = 16
+_PLAN_PINS: Optional[list] = None      # while a CUDA graph is being captured (jmac_b200.graphs): every plan handed out is also kept here,
+                                       # so that the captured kernels' plan arrays outlive an eviction from the LRU cache
 
 
 def get_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int) -> GraphPlan:
@@ -107,12 +109,16 @@ def get_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_
     hit = _PLAN_CACHE.get(key)
     if hit is not None:
         _PLAN_CACHE.move_to_end(key)
+        if _PLAN_PINS is not None:
+            _PLAN_PINS.append(hit[0])
         return hit[0]
     plan = GraphPlan(edge_index, edge_type, num_ent, n_rel)
     # keep the key tensors alive so that their addresses cannot be recycled while cached
     _PLAN_CACHE[key] = (plan, edge_index, edge_type)
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
         _PLAN_CACHE.popitem(last=False)
+    if _PLAN_PINS is not None:
+        _PLAN_PINS.append(plan)
     return plan
 
 
@@ -296,11 +302,18 @@ def attn_edge(plan, X, W_att, Rp, a_att, slope, X_src=None):
 # ----------------------------------------------------------------------------------------------
 # node-level dense products (3xTF32 on tcgen05, fp32-accurate)
 # ----------------------------------------------------------------------------------------------
+import os as _os
+_GEMM_MODE = int(_os.environ.get("JMAC_GEMM_MODE", "0"))
+
+
 def _split_tf32(w_nk: torch.Tensor):
     """hi = w rounded to nearest TF32 (ties away, like cvt.rna.tf32.f32; low 13 mantissa bits zero),
     lo = w - hi (exact in fp32)."""
     hi = ((w_nk.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
-    return hi, w_nk - hi
+    lo = w_nk - hi
+    if _GEMM_MODE & 1:          # lo rounded to TF32 as well: nothing is left for the tensor core to truncate
+        lo = ((lo.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return hi, lo
 
 
 def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
@@ -462,6 +475,8 @@ class TransEMarginFn(torch.autograd.Function):
         _need_cuda(*ents, *rels)
         dev = ents[0].device
         d = ents[0].shape[1]
+        if any(e.shape != ents[0].shape for e in ents) or any(r.shape != rels[0].shape for r in rels):
+            raise ValueError("every layer's entity (relation) table must have the same shape: one index list addresses all of them")
         h, r, t = as_index(h, dev), as_index(r, dev), as_index(t, dev)
         M = int(h.numel())
         if int(r.numel()) != M or int(t.numel()) != M:

@@ -260,13 +260,27 @@ class JMAC(BaseModel):
         return total / (2 * self.k * n) * 1
 
     def forward_linkpred(self, e_index, r_index, edge_index, edge_type, all_index, ent_bases, rel_bases, pred_head=False):
-        """:295-313.  ``all_index`` is ``list(range(N))`` at every call site (src/validate.py:44)."""
+        """:295-313.  ``all_index`` is ``list(range(N))`` at every call site (src/validate.py:44); any other index list
+        selects / permutes the table first, as the reference's ``ent[all_index]`` does (:304).
+        The [B,N] distances come from ``jmac_l1_dist``; when a gradient is requested through them (the reference's result
+        carries one, although no caller uses it) they are formed by the differentiable library ``torch.cdist`` instead."""
         _, ents, rels = self.forward_base(edge_index, edge_type, ent_bases, rel_bases)
         L = self.args.num_gcn_layer
         n = ents[0].shape[0]
-        if len(all_index) != n or (n > 0 and (all_index[0] != 0 or all_index[-1] != n - 1)):
+        identity = isinstance(all_index, range) and all_index == range(n)
+        if not identity:
+            ai = np.asarray(all_index.cpu() if torch.is_tensor(all_index) else all_index)
+            identity = ai.shape == (n,) and bool(np.array_equal(ai, np.arange(n)))
+        if not identity:
             idx = JF.as_index(all_index, ents[0].device)
-            ents = [e[idx] for e in ents]
+            ents = [e[idx] for e in ents]                  # all_kg_emb = ent[all_index] (:304); e_index addresses THIS table (:306)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in list(ents[:L]) + list(rels[:L])):
+            ei, ri = JF.as_index(e_index, ents[0].device), JF.as_index(r_index, ents[0].device)
+            dist = 0
+            for e, r in zip(ents[:L], rels[:L]):
+                er = e[ei] - r[ri] if pred_head else e[ei] + r[ri]
+                dist = dist + torch.cdist(er, e, p=1)
+            return dist
         return JF.l1_dist(ents[:L], rels[:L], e_index, r_index, pred_head)
 
     def completion_loss(self, data, edge_index1, edge_type1, edge_index2, edge_type2, feeddict, source=True):
@@ -297,9 +311,18 @@ class JMAC(BaseModel):
         return losses
 
     def _margin(self) -> float:
-        # margin_completion is a frozen Parameter (:156-157); cache its value to avoid a device sync per step
+        # margin_completion is a frozen Parameter (:156-157); its value is cached to avoid a device sync per step and
+        # dropped whenever the parameter object can have changed (load_state_dict, .to() / .cuda() / .double())
         m = getattr(self, "_margin_cache", None)
         if m is None:
             m = float(self.margin_completion.detach().cpu().item())
             self._margin_cache = m
         return m
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._margin_cache = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._margin_cache = None
+        return super()._apply(fn, *args, **kwargs)

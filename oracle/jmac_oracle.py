@@ -38,7 +38,7 @@ import torch.nn.functional as F
 def scatter_sum(src: torch.Tensor, index: torch.Tensor, dim_size: int) -> torch.Tensor:
     """``torch_scatter.scatter(src, index, dim=0, dim_size=dim_size, reduce='sum')``: rows of
     ``src`` are summed into ``out[index[e]]``; groups with no member stay zero."""
-    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     if src.numel():
         out.index_add_(0, index, src)
     return out
@@ -50,7 +50,7 @@ def scatter_softmax(src: torch.Tensor, index: torch.Tensor, dim_size: int) -> to
     if src.numel() == 0:
         return src.clone()
     idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
-    gmax = torch.full((dim_size,) + tuple(src.shape[1:]), -math.inf, dtype=src.dtype)
+    gmax = torch.full((dim_size,) + tuple(src.shape[1:]), -math.inf, dtype=src.dtype, device=src.device)
     gmax = gmax.scatter_reduce(0, idx, src.detach(), reduce="amax", include_self=True)
     shifted = src - gmax[index]
     ex = shifted.exp()
@@ -81,7 +81,7 @@ class BNState:
 
 def compute_norm(row: torch.Tensor, num_ent: int, dtype) -> torch.Tensor:
     """src/jmac_model.py:99-109 -- deg^-1/2 of the aggregation target of every edge (inf -> 0)."""
-    deg = scatter_sum(torch.ones(row.shape[0], dtype=dtype), row, num_ent)
+    deg = scatter_sum(torch.ones(row.shape[0], dtype=dtype, device=row.device), row, num_ent)
     deg_inv = deg.pow(-0.5)
     deg_inv[deg_inv == float("inf")] = 0
     return deg_inv[row]
@@ -139,9 +139,9 @@ def relation_aware_layer(p: Dict[str, torch.Tensor], ent_emb, rel_emb, edge_inde
     rel = rel @ p["rel_transform_weight1"]                                  # :40
     rel = leaky_relu(rel, slope) if rel_act == "leaky" else torch.relu(rel)  # :41
     rel = rel @ p["rel_transform_weight2"]                                  # :42
-    loop = torch.arange(num_ent)
+    loop = torch.arange(num_ent, device=ent_emb.device)
     loop_index = torch.stack([loop, loop])                                  # :44
-    loop_type = torch.full((num_ent,), rel.shape[0] - 1, dtype=torch.long)  # :45
+    loop_type = torch.full((num_ent,), rel.shape[0] - 1, dtype=torch.long, device=ent_emb.device)  # :45
     norm = compute_norm(edge_index[0], num_ent, ent_emb.dtype)              # :47
     neigh = propagate(p, ent_emb, rel, edge_index, edge_type, norm, num_ent, slope, comp_op)   # :49
     selfm = propagate(p, ent_emb, rel, loop_index, loop_type, None, num_ent, slope, comp_op)   # :50
@@ -183,7 +183,7 @@ def alignment_loss_simple(links, emb1, emb2):
     """JMAC.alignment_loss_simple (src/jmac_model.py:237-249)."""
     if not len(links):
         return 0
-    links = torch.as_tensor(np.asarray(links)).long()
+    links = torch.as_tensor(np.asarray(links)).long().to(emb1.device)
     a = F.normalize(emb1[links[:, 0]], 2, -1)
     b = F.normalize(emb2[links[:, 1]], 2, -1)
     return (1 - (a * b).sum(1)).mean()
@@ -197,7 +197,7 @@ def transe_margin(ent, rel, batch_h, batch_r, batch_t, batch_size: int, margin: 
     pos = pos.view(-1, min(batch_size, len(pos))).permute(1, 0)
     neg = score[batch_size:]
     neg = neg.view(-1, min(batch_size, len(neg))).permute(1, 0)
-    m = torch.tensor([margin], dtype=score.dtype)
+    m = torch.tensor([margin], dtype=score.dtype, device=score.device)
     return torch.max(pos - neg, -m).mean() + m, score
 
 
@@ -338,9 +338,29 @@ def greedy_alignment(e1, e2, top_k=(1, 5, 10), metric="cosine", normalize=False,
     return list(top_k), hits, mr, mrr, ranks, top1
 
 
+def greedy_alignment_torch(e1: torch.Tensor, e2: torch.Tensor, top_k=(1, 5, 10), csls_k=10):
+    """The same evaluation (metric='cosine', accurate=True) as dense torch ops on the tensors' device: float64 cosine
+    (cdist semantics, similarity.py:44-46) -> float32, CSLS from the means of the k largest per row / column
+    (similarity.py:58-84), rank of the gold column in a full descending argsort of every row (alignment.py:99-104).
+    This is the "reference algorithm in PyTorch eager" that bench.py times on the GPU next to the streaming kernel;
+    it materialises the n1 x n2 matrix like the reference does.  Returns (hits%, mr, mrr, ranks[0-based])."""
+    a, b = e1.double(), e2.double()
+    s = (1.0 - (1.0 - (a @ b.t()) / (a.norm(dim=1)[:, None] * b.norm(dim=1)[None, :]))).float()
+    if csls_k > 0:
+        r1 = s.topk(csls_k, dim=1)[0].mean(1)
+        r2 = s.topk(csls_k, dim=0)[0].mean(0)
+        s = (2 * s.t() - r1).t() - r2
+    order = torch.argsort(s, dim=1, descending=True)
+    gold = torch.arange(s.shape[0], device=s.device)
+    ranks = (order == gold[:, None]).int().argmax(1)
+    n = s.shape[0]
+    hits = [float((ranks < k).sum()) / n * 100 for k in top_k]
+    return hits, float((ranks + 1).sum()) / n, float((1.0 / (ranks + 1).double()).sum()) / n, ranks
+
+
 def get_neg(ILL, emb_src: torch.Tensor, emb_dst: torch.Tensor, k: int) -> torch.Tensor:
     """get_neg (modules/utils/util.py:31-54): top-k most similar entities of emb_dst per seed."""
-    ILL = torch.as_tensor(np.asarray(ILL)).long()
+    ILL = torch.as_tensor(np.asarray(ILL)).long().to(emb_src.device)
     s = emb_src[ILL] @ emb_dst.t()
     return s.topk(k, dim=1)[1].reshape(len(ILL) * k)
 
@@ -348,17 +368,17 @@ def get_neg(ILL, emb_src: torch.Tensor, emb_dst: torch.Tensor, k: int) -> torch.
 def compute_alignment_quality(e1: torch.Tensor, e2: torch.Tensor, list1, list2, scale=20.0):
     """compute_alignment_quality (train.py:231-259).  Returns (entropy, softmax_simi,
     softmax_simi2) exactly as the reference (dense N1xN2 -- small cases only)."""
-    l1 = torch.as_tensor(np.asarray(list1)).long()
-    l2 = torch.as_tensor(np.asarray(list2)).long()
+    l1 = torch.as_tensor(np.asarray(list1)).long().to(e1.device)
+    l2 = torch.as_tensor(np.asarray(list2)).long().to(e1.device)
     s = e1[l1] @ e2[l2].t()
     p1 = torch.softmax(s * scale, dim=1)
     h1 = (-torch.log(p1) * p1).sum(1).mean()
     p2 = torch.softmax(s.t() * scale, dim=1)
     h2 = (-torch.log(p2) * p2).sum(1).mean()
     full = e1 @ e2.t()
-    m1 = torch.ones(e1.shape[0], dtype=torch.bool)
+    m1 = torch.ones(e1.shape[0], dtype=torch.bool, device=e1.device)
     m1[l1] = False
-    m2 = torch.ones(e2.shape[0], dtype=torch.bool)
+    m2 = torch.ones(e2.shape[0], dtype=torch.bool, device=e1.device)
     m2[l2] = False
     full[m1] = -1
     full[:, m2] = -1

@@ -6,8 +6,9 @@ Real degree distribution: in-degree max 481-2,769 against a mean of 3-7, 6-37 % 
 
 Tolerances: fp32 1e-4 relative on losses/embeddings before any optimiser step; Adam amplifies rounding noise on
 near-zero gradients (update = lr * g / (|g| + eps)), so quantities after k steps get k * lr-sized slack.
-Alignment metrics come from bf16-rounded inputs: Hits@k may move by the rows whose gold score sits inside
-the bf16 band (documented ties)."""
+Alignment metrics, get_neg and compute_alignment_quality run in the default fp32-accurate (3xTF32) mode of the
+similarity kernel: what separates them from the reference's numbers is only the ~1e-5 fp32 noise of the embeddings
+themselves (documented ties)."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -181,21 +182,32 @@ def test_alignment_metrics_and_negatives(trace):
     n = len(g["test_links"])
     for tag in ("before", "after"):
         got, ref = trace[tag]["metrics"], g[f"{tag}.align_metrics"]
-        rows = 4 if tag == "before" else 10      # the reference's own run-to-run spread after training is 2 rows (threaded scatter order)
+        # before training the inputs agree to ~1e-5 (fp32 encoder noise): at most 2 rows may cross a Hits@k boundary; after nine Adam
+        # steps the reference's own run-to-run spread is 2 rows (threaded scatter order) and Adam spreads rounding noise (see above)
+        rows = 2 if tag == "before" else 10
         assert np.all(np.abs(got[:3] - ref[:3]) <= 100.0 * rows / n + 1e-9), (tag, got, ref)    # rows crossing a Hits@k boundary
-        assert abs(got[3] - ref[3]) <= 0.02 * ref[3] and abs(got[4] - ref[4]) <= 0.1 * ref[4] + 1e-3, (tag, got, ref)
-    # get_neg: the reference's neighbours and ours are the same sets up to the bf16 band -- compare by similarity value
+        mr_tol, mrr_tol = (2e-3, 5e-3) if tag == "before" else (0.02, 0.1)
+        assert abs(got[3] - ref[3]) <= mr_tol * ref[3] and abs(got[4] - ref[4]) <= mrr_tol * ref[4] + 1e-4, (tag, got, ref)
+    # get_neg: the reference's neighbours and ours are the same sets wherever the 25th and 26th neighbour are further apart than
+    # the fp32 noise of the embeddings; the similarity values of the chosen neighbours agree to that noise
     o1 = trace["before"]["emb1"].double().cpu().numpy()
     o2 = trace["before"]["emb2"].double().cpu().numpy()
     src = g["links"][:, 0]
     S = o1[src] @ o2.T
-    ours = np.sort(S[np.arange(len(src))[:, None], trace["neg_right"].reshape(-1, K)], axis=1)
-    refs = np.sort(S[np.arange(len(src))[:, None], g["neg_right"].reshape(-1, K)], axis=1)
+    ours_i, refs_i = trace["neg_right"].reshape(-1, K), g["neg_right"].reshape(-1, K)
+    ours = np.sort(S[np.arange(len(src))[:, None], ours_i], axis=1)
+    refs = np.sort(S[np.arange(len(src))[:, None], refs_i], axis=1)
     scale = float(np.abs(S).max())
-    assert float(np.abs(ours - refs).max()) <= 1e-2 * scale                  # bf16 inputs: |delta S| <= 2^-8 * |a||b|
+    assert float(np.abs(ours - refs).max()) <= 3e-5 * scale
+    srt = -np.sort(-S, axis=1)
+    clear = (srt[:, K - 1] - srt[:, K]) > 3e-5 * scale
+    assert clear.mean() > 0.9
+    assert np.array_equal(np.sort(ours_i[clear], 1), np.sort(refs_i[clear], 1))           # identical index sets modulo documented ties
     ent, rowmax, rowarg = trace["caq"]
-    np.testing.assert_allclose(ent, float(g["caq_entropy"]), rtol=2e-3)
-    np.testing.assert_allclose(rowmax, g["caq_rowmax"], rtol=0.1, atol=1e-4)
+    np.testing.assert_allclose(ent, float(g["caq_entropy"]), rtol=5e-4)
+    np.testing.assert_allclose(rowmax, g["caq_rowmax"], rtol=2e-3, atol=1e-6)
+    sure = g["caq_rowmax"] > 0.5                                                            # an argmax holding most of the mass cannot flip
+    assert np.array_equal(rowarg[sure], g["caq_rowarg"][sure])
 
 
 def test_filtered_link_prediction_metrics(trace):
