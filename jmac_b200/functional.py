@@ -393,7 +393,7 @@ def node_mm(X: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 class BNTanhFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pre, gamma, beta, running_mean, running_var, momentum, eps, training, group):
+    def forward(ctx, pre, gamma, beta, running_mean, running_var, momentum, eps, training, group, n_global=None):
         _need_cuda(pre, gamma, beta)
         lib = _lib.load()
         pre, gamma, beta = _f32c(pre), _f32c(gamma), _f32c(beta)
@@ -409,10 +409,11 @@ class BNTanhFn(torch.autograd.Function):
             if training:
                 sums = torch.zeros(2 * d + 1, dtype=torch.float64, device=dev)
                 check(lib.jmac_bn_stats(ptr(pre), N, d, ptr(sums), st), "jmac_bn_stats")
-                if group is not None:  # BN is over ALL nodes: all-reduce (sum x, sum x^2, n) across destination shards
-                    sums[2 * d] = float(N)
+                if group is not None:  # BN is over ALL nodes: all-reduce (sum x, sum x^2) across destination shards
+                    if n_global is None:
+                        raise ValueError("sharded BatchNorm needs the global row count (a constant of the partition: Shard.n_total)")
                     torch.distributed.all_reduce(sums, group=group)
-                    n_total = int(round(float(sums[2 * d].item())))
+                    n_total = int(n_global)
                 st = stream_ptr()
             check(lib.jmac_bn_tanh_apply(ptr(pre), N, d, ptr(sums), n_total, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                                          float(momentum), float(eps), int(bool(training)), ptr(out), ptr(mean), ptr(rstd), st),
@@ -446,11 +447,13 @@ class BNTanhFn(torch.autograd.Function):
                                              ctx.n_total, int(ctx.training), ptr(gpre), None, None, st), "jmac_bn_tanh_bwd_apply")
         dbeta = local[:d].to(torch.float32)
         dgamma = local[d:].to(torch.float32)
-        return gpre, dgamma, dbeta, None, None, None, None, None, None
+        return gpre, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def bn_tanh(pre, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, training=True, group=None):
-    return BNTanhFn.apply(pre, gamma, beta, running_mean, running_var, momentum, eps, training, group)
+def bn_tanh(pre, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, training=True, group=None, n_global=None):
+    """tanh(BatchNorm1d(pre)) over the node dimension.  ``group`` + ``n_global``: the rows are one destination shard of
+    ``n_global`` nodes; the per-feature sums are all-reduced over ``group`` (no host synchronisation)."""
+    return BNTanhFn.apply(pre, gamma, beta, running_mean, running_var, momentum, eps, training, group, n_global)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -55,12 +55,21 @@ class CpuOps:
         return agg if Xself is None else agg + Xself - Rp[-1]
 
     @staticmethod
-    def bn_tanh(pre, gamma, beta, rm, rv, momentum, eps, training, group):
+    def bn_tanh(pre, gamma, beta, rm, rv, momentum, eps, training, group, n_global):
         n = torch.tensor([float(pre.shape[0])], dtype=pre.dtype)
         dist.all_reduce(n, group=group)
+        assert int(n.item()) == n_global
         mean = _AllReduceSum.apply(pre.sum(0), group) / n
         var = _AllReduceSum.apply(((pre - mean) ** 2).sum(0), group) / n
         return torch.tanh((pre - mean) / torch.sqrt(var + eps) * gamma + beta)
+
+    @staticmethod
+    def as_index(x, device):
+        return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).long()
+
+    @staticmethod
+    def transe_margin_loss(ents, rels, h, r, t, batch_size, margin):
+        return torch.stack([O.transe_margin(e, rl, h, r, t, batch_size, margin)[0].reshape(()) for e, rl in zip(ents, rels)])
 
 
 def make_layer(d, seed):
@@ -74,7 +83,7 @@ def make_layer(d, seed):
     return layer
 
 
-def _worker(rank, world, port, N, E, R, d):
+def _worker(rank, world, port, N, E, R, d, chunks):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -97,8 +106,9 @@ def _worker(rank, world, port, N, E, R, d):
             h = O.relation_aware_layer(pl, h, ro, ei, et, slope=0.05, bn_state=None, training=True)
         h.backward(gout)
         # ---- sharded
-        enc = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD, ops=CpuOps)
+        enc = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD, ops=CpuOps, chunks=chunks)
         sh = enc.shard
+        assert sh.chunks == chunks and sh.n_max % chunks == 0 and sh.n_total == N
         assert sh.bounds[0] == 0 and sh.bounds[-1] == N and all(b1 > b0 for b0, b1 in zip(sh.bounds, sh.bounds[1:]))
         deg = np.bincount(row, minlength=N)
         assert sh.edge_index.shape[1] == deg[sh.lo:sh.hi].sum()       # every in-edge of an owned node, nothing else
@@ -118,16 +128,67 @@ def _worker(rank, world, port, N, E, R, d):
         assert full.shape[0] == world * sh.n_max
         for g in range(world):
             ng = sh.bounds[g + 1] - sh.bounds[g]
-            assert torch.all(full[g * sh.n_max: g * sh.n_max + ng] == g + 1)
+            assert torch.all(full[sh.gathered_row(g, torch.arange(ng))] == g + 1)       # chunk-major layout of the gathered table
+        # the local re-layout of a replicated table (first layer: no communication) is the same table
+        rep = torch.arange(N, dtype=torch.float64).view(N, 1).repeat(1, 2)
+        got = JD.GatherRowsFn.apply(rep[sh.lo:sh.hi].clone(), sh, dist.group.WORLD)
+        loc_layout = rep.index_select(0, sh.gather_map("cpu"))
+        for g in range(world):
+            rows = sh.gathered_row(g, torch.arange(sh.bounds[g + 1] - sh.bounds[g]))
+            assert torch.equal(got[rows], loc_layout[rows])
         full.sum().backward()
         assert torch.all(loc.grad == world)                            # every rank contributed a 1 for each of my rows
+
+        # ---- data-parallel completion scorer on row-sharded encoder outputs + a replicated parameter table
+        B, K = 10, 3
+        hb, rb = rng.integers(0, N, B), rng.integers(0, R, B)
+        bh, br = np.tile(hb, K + 1), np.tile(rb, K + 1)
+        bt = rng.integers(0, N, (K + 1) * B)
+        e0 = x.clone().requires_grad_(True)                            # replicated leaf (the embedding parameter slice)
+        e1_full = (x * 0.5 + 1.0).clone().requires_grad_(True)          # stands for the encoder output: every rank owns rows [lo, hi)
+        e1_loc = e1_full.detach()[sh.lo:sh.hi].clone().requires_grad_(True)
+        rt = [rel.clone().requires_grad_(True), (rel * 2).clone().requires_grad_(True)]
+        ref = torch.stack([O.transe_margin(e, rl, T(bh), T(br), T(bt), B, 5.0)[0].reshape(()) for e, rl in zip([e0, e1_full], rt)])
+        ref.sum().backward()
+        ref_g = [e0.grad.clone(), e1_full.grad.clone(), rt[0].grad.clone(), rt[1].grad.clone()]
+        for v in [e0, e1_full] + rt:
+            v.grad = None
+        e1_g = JD.GatherRowsFn.apply(e1_loc, sh, dist.group.WORLD)
+        e1_tab = e1_g.index_select(0, sh.gathered_row(torch.bucketize(torch.arange(N), torch.tensor(sh.bounds)[1:], right=True),
+                                                      torch.arange(N) - torch.tensor(sh.bounds)[torch.bucketize(torch.arange(N), torch.tensor(sh.bounds)[1:], right=True)]))
+        loss = JD.sharded_transe_margin_loss([e0, e1_tab], rt, bh, br, bt, B, 5.0, dist.group.WORLD, ops=CpuOps)
+        np.testing.assert_allclose(loss.detach().numpy(), ref.detach().numpy(), atol=1e-12)     # same value on every rank
+        loss.sum().backward()
+        JD.all_reduce_grads([e0] + rt, dist.group.WORLD)
+        np.testing.assert_allclose(e0.grad.numpy(), ref_g[0].numpy(), atol=1e-12)
+        np.testing.assert_allclose(e1_loc.grad.numpy(), ref_g[1].numpy()[sh.lo:sh.hi], atol=1e-12)   # reduce-scattered to the owner
+        np.testing.assert_allclose(rt[0].grad.numpy(), ref_g[2].numpy(), atol=1e-12)
+        np.testing.assert_allclose(rt[1].grad.numpy(), ref_g[3].numpy(), atol=1e-12)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_encoder_matches_oracle_gloo(world):
-    mp.spawn(_worker, args=(world, _free_port(), 61, 400, 5, 16), nprocs=world, join=True)
+def T(a):
+    return torch.from_numpy(np.asarray(a).astype(np.int64))
+
+
+@pytest.mark.parametrize("world,chunks", [(2, 1), (3, 1), (2, 3), (3, 2)])
+def test_sharded_encoder_matches_oracle_gloo(world, chunks):
+    mp.spawn(_worker, args=(world, _free_port(), 61, 400, 5, 16, chunks), nprocs=world, join=True)
+
+
+def test_positive_share_covers_the_batch():
+    from jmac_b200.dist import positive_share
+    for B, K1, world in ((10, 4, 3), (7, 2, 8), (1000, 26, 4)):
+        M = B * K1
+        seen = []
+        for r in range(world):
+            Bq, b0, b1, sel = positive_share(B, M, r, world)
+            assert Bq == B and sel.numel() == (b1 - b0) * K1
+            # re-laid-out share keeps the reference pairing: position k * B_r + j is triple k * B + (b0 + j)
+            assert torch.equal(sel.view(K1, b1 - b0), torch.arange(K1)[:, None] * B + torch.arange(b0, b1)[None, :])
+            seen.append(sel)
+        assert torch.equal(torch.sort(torch.cat(seen))[0], torch.arange(M))
 
 
 def test_partition_balances_in_edges():
@@ -154,4 +215,7 @@ def test_partition_balances_in_edges():
             back = torch.tensor(sh.bounds)[owner] + sh.edge_index[1] % sh.n_max
             mine = (row >= sh.lo) & (row < sh.hi)
             assert torch.equal(back, col[mine])
+            # chunked gathered layout: the replicated table re-laid-out through gather_map holds the right row under every edge
+            sh3 = build_shard(torch.stack([row, col]), et, N, g, world, chunks=3)
+            assert sh3.n_max % 3 == 0 and torch.equal(sh3.gather_map("cpu")[sh3.edge_index[1]], col[mine])
         assert tot == E

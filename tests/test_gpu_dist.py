@@ -1,5 +1,7 @@
-"""Multi-GPU (NCCL) parity: the destination-sharded encoder and the row-sharded alignment evaluation on 2 GPUs against the single-GPU CUDA
-path on the same inputs.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box."""
+"""Multi-GPU (NCCL) parity on 2 GPUs: the destination-sharded encoder (composed path, fused path with chunked overlapped
+exchange) against the float64 ORACLE with the gradient budget of SURVEY 8c, the data-parallel completion scorer against
+the single-GPU scorer, and the row-sharded alignment evaluation against the single-GPU one.
+Needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box (bench.py prints the same parity numbers at every N > 1)."""
 import os
 import socket
 
@@ -25,54 +27,102 @@ def _make_layers(d):
     return [RelationAwareLayer(d, d, rel_dim=d, act=torch.tanh, args=SimpleNamespace(leaky_relu_w=0.05, comp_op="sub")) for _ in range(2)]
 
 
-def _worker(rank, world, port, N, E, R, d):
+def _rel_err(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def _worker(rank, world, port, N, E, R, d, chunks):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from jmac_b200 import dist as JD
+        from oracle import jmac_oracle as O
         rng = np.random.default_rng(0)
         row, col, typ = rng.integers(0, N, E), rng.integers(0, N, E), rng.integers(0, R, E)
         row[: E // 5] = 11
         ei, et = torch.from_numpy(np.stack([row, col])).to(dev), torch.from_numpy(typ).to(dev)
         torch.manual_seed(1)
         x, rel, gout = torch.randn(N, d) * 0.5, torch.randn(R, d) * 0.5, torch.randn(N, d)
-        # single-GPU reference (each rank computes it on its own device)
-        ref_layers = [l.to(dev) for l in _make_layers(d)]
-        xs, rs = x.to(dev).requires_grad_(True), rel.to(dev).requires_grad_(True)
-        h = ref_layers[1](ref_layers[0](xs, rs, ei, et), rs, ei, et)
-        h.backward(gout.to(dev))
-        # sharded
+        # ---- arbiter: the oracle (reference algorithm) in float64 on this device, and in float32 for the budget
+        base = [l.to(dev) for l in _make_layers(d)]
+
+        def oracle(dtype):
+            p = [{k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in l.named_parameters()} for l in base]
+            xo, ro = x.to(dev, dtype).requires_grad_(True), rel.to(dev, dtype).requires_grad_(True)
+            h = xo
+            for pl in p:
+                h = O.relation_aware_layer(pl, h, ro, ei, et, slope=0.05, bn_state=None, training=True)
+            h.backward(gout.to(dev, dtype))
+            return h.detach(), xo.grad, ro.grad, p
+        h64, dx64, dr64, p64 = oracle(torch.float64)
+        h32, dx32, dr32, p32 = oracle(torch.float32)
+        # ---- sharded
         layers = [l.to(dev) for l in _make_layers(d)]
-        enc = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD)
+        enc = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD, chunks=chunks)
         rg = rel.to(dev).requires_grad_(True)
         out = enc.step(x.to(dev), rg, gout.to(dev))
         sh = enc.shard
-        torch.testing.assert_close(out, h.detach()[sh.lo:sh.hi], atol=1e-4, rtol=1e-4)   # two stacked layers; the hub row (sqrt(deg) = 110) amplifies fp32 path differences
+        torch.testing.assert_close(out.double(), h64[sh.lo:sh.hi], atol=1e-4, rtol=1e-4)   # two stacked layers; the hub row (sqrt(deg) = 110) amplifies fp32 path differences
 
-        def close(a, b, name):
-            err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
-            assert err < 1e-2, f"{name}: rel err {err:.2e}"      # fp32-vs-fp32: each side carries ~1e-3 softmax-backward cancellation noise
+        def budget(got, ref64, ref32, name):
+            # err(new) <= max(1e-4, 4 x err(reference-fp32)), both measured against the float64 run.  Two stacked layers:
+            # a LeakyReLU sign decision of the second layer that differs from float64 (tests/budget.py) spreads through the first
+            # layer's backward, so beyond the budget only a sliver of rows may move, each by a small fraction of the largest entry
+            err_new, err_ref = _rel_err(got, ref64), _rel_err(ref32, ref64)
+            tol = max(1e-4, 4 * err_ref)
+            if err_new > tol:
+                a, b = got.double(), ref64.double()
+                row_err = (a - b).abs().reshape(a.shape[0], -1).amax(1) / b.abs().max().clamp_min(1e-30)
+                assert float((row_err > tol).float().mean()) <= 2e-3 and float(row_err.max()) <= 5e-2, \
+                    f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}, {int((row_err > tol).sum())} rows out of budget"
 
-        close(enc._x_loc.grad, xs.grad[sh.lo:sh.hi], "dX")
-        close(rg.grad, rs.grad, "dR")
-        for l, lr in zip(layers, ref_layers):
-            for (k, v), (_, vr) in zip(l.named_parameters(), lr.named_parameters()):
+        budget(enc._x_loc.grad, dx64[sh.lo:sh.hi], dx32[sh.lo:sh.hi], "dX")
+        budget(rg.grad, dr64, dr32, "dR")
+        for l, pl64, pl32 in zip(layers, p64, p32):
+            for k, v in l.named_parameters():
                 if k == "loop_rel":
-                    continue                                       # mathematically zero (fp32 noise only)
-                close(v.grad, vr.grad, k)
-            torch.testing.assert_close(l.bn.running_mean, lr.bn.running_mean, atol=1e-6, rtol=1e-5)
-            torch.testing.assert_close(l.bn.running_var, lr.bn.running_var, atol=1e-6, rtol=1e-5)
+                    assert float(v.grad.abs().max()) <= 2e-3        # mathematically zero (BatchNorm removes constants): fp32 noise only
+                    continue
+                budget(v.grad, pl64[k].grad, pl32[k].grad, k)
+        # ---- data-parallel completion scorer on the sharded encoder output + the replicated input table
+        from jmac_b200 import functional as JF
+        B, K = 64, 8
+        hb, rb = rng.integers(0, N, B), rng.integers(0, R, B)
+        bh, br, bt = np.tile(hb, K + 1), np.tile(rb, K + 1), rng.integers(0, N, (K + 1) * B)
+        T = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+        e0 = x.to(dev).requires_grad_(True)
+        e1_full = h32.clone().requires_grad_(True)
+        rt = [rel.to(dev).requires_grad_(True), (rel.to(dev) * 2).requires_grad_(True)]
+        ref = JF.transe_margin_loss([e0, e1_full], rt, T(bh), T(br), T(bt), B, 5.0)
+        ref.sum().backward()
+        ref_g = [e0.grad.clone(), e1_full.grad.clone(), rt[0].grad.clone(), rt[1].grad.clone()]
+        for v in [e0, e1_full] + rt:
+            v.grad = None
+        e1_loc = h32[sh.lo:sh.hi].clone().requires_grad_(True)
+        owner = torch.bucketize(torch.arange(N), torch.tensor(sh.bounds)[1:], right=True)
+        rows = sh.gathered_row(owner, torch.arange(N) - torch.tensor(sh.bounds)[owner]).to(dev)
+        e1_tab = JD.GatherRowsFn.apply(e1_loc, sh, dist.group.WORLD).index_select(0, rows)
+        loss = JD.sharded_transe_margin_loss([e0, e1_tab], rt, T(bh), T(br), T(bt), B, 5.0, dist.group.WORLD)
+        torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-6)
+        loss.sum().backward()
+        JD.all_reduce_grads([e0] + rt, dist.group.WORLD)
+        torch.testing.assert_close(e0.grad, ref_g[0], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(e1_loc.grad, ref_g[1][sh.lo:sh.hi], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(rt[0].grad, ref_g[2], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(rt[1].grad, ref_g[3], rtol=1e-4, atol=1e-6)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("N,E", [(5000, 60000),          # shards below 4096 rows: composed path (library GEMMs for the local rows)
-                                 (12000, 100001)])       # shards of ~6000 rows: the fused attention-input node on a gathered source table
-def test_sharded_encoder_matches_single_gpu_nccl(N, E):
-    mp.spawn(_worker, args=(2, _free_port(), N, E, 30, 256), nprocs=2, join=True)
+@pytest.mark.parametrize("N,E,chunks", [(5000, 60000, 1),       # shards below 4096 rows: composed path (library GEMMs, GatherRowsFn through autograd)
+                                        (12000, 100001, 1),    # shards of ~6000 rows: ShardedAttnEdgeFn, one exchange per layer
+                                        (20000, 150001, 2),    # ... two chunks per exchange, overlapped with the chunk GEMMs
+                                        (40000, 250001, None)])  # default chunking (4)
+def test_sharded_encoder_matches_oracle_nccl(N, E, chunks):
+    mp.spawn(_worker, args=(2, _free_port(), N, E, 30, 256, chunks), nprocs=2, join=True)
 
 
 def _align_worker(rank, world, port, n1, n2, d, csls):

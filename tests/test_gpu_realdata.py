@@ -198,11 +198,18 @@ def test_alignment_metrics_and_negatives(trace):
     ours = np.sort(S[np.arange(len(src))[:, None], ours_i], axis=1)
     refs = np.sort(S[np.arange(len(src))[:, None], refs_i], axis=1)
     scale = float(np.abs(S).max())
-    assert float(np.abs(ours - refs).max()) <= 3e-5 * scale
-    srt = -np.sort(-S, axis=1)
-    clear = (srt[:, K - 1] - srt[:, K]) > 3e-5 * scale
-    assert clear.mean() > 0.9
-    assert np.array_equal(np.sort(ours_i[clear], 1), np.sort(refs_i[clear], 1))           # identical index sets modulo documented ties
+    band = 3e-5 * scale
+    assert float(np.abs(ours - refs).max()) <= band
+    # identical index SETS modulo documented ties: an index chosen by only one side must score within the band of the row's 25th value
+    kth = -np.sort(-S, axis=1)[:, K - 1]
+    rows = np.arange(len(src))[:, None]
+    in_ours = np.zeros_like(S, dtype=bool)
+    in_refs = np.zeros_like(S, dtype=bool)
+    in_ours[rows, ours_i] = True
+    in_refs[rows, refs_i] = True
+    only_one = in_ours ^ in_refs
+    assert np.all(np.abs(S - kth[:, None])[only_one] <= band)
+    assert (only_one.sum(1) == 0).mean() > 0.9                                              # and most rows agree outright
     ent, rowmax, rowarg = trace["caq"]
     np.testing.assert_allclose(ent, float(g["caq_entropy"]), rtol=5e-4)
     np.testing.assert_allclose(rowmax, g["caq_rowmax"], rtol=2e-3, atol=1e-6)
