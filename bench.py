@@ -586,7 +586,7 @@ def run_b200(args):
         ia = torch.randint(0, N, (npair,), device=dev)
         ib = torch.randint(0, N, (npair,), device=dev)
         cosv = torch.empty(npair, device=dev)
-        k_gather = lambda: _lib.check(lib.jmac_pair_cos_fwd(ptr(X), ptr(gout), d, ptr(ia), ptr(ib), npair, ptr(cosv), st()))
+        k_gather = lambda: _lib.check(lib.jmac_pair_cos_fwd(ptr(X), ptr(gout), d, ptr(ia), ptr(ib), npair, N, N, ptr(cosv), st()))
         t_g = event_time(k_gather, 3, 10)
         gather_gbps = npair * (2 * row + 20) / t_g / 1e6
         del ia, ib, cosv

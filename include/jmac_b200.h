@@ -33,6 +33,12 @@ const char* jmac_version(void);
 const char* jmac_last_error(void);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t jmac_launch_count(void);
+/* Asynchronous index errors.  The scorer / pair-cosine / link-prediction kernels take index lists straight from the caller
+ * (the reference raises IndexError / a device-side assert on a bad one).  They never read or write out of bounds: an index
+ * outside its table is replaced by row 0 and a flag is raised in mapped host memory.  jmac_status_poll returns and clears
+ * the flags WITHOUT synchronising (bit 0: triple scorer h/r/t, bit 1: pair cosine ia/ib, bit 2: link prediction e/r/t/filter);
+ * synchronise the stream first to be sure the kernels in question have run. */
+int jmac_status_poll(void);
 
 /* ------------------------------------------------------------------------------------------
  * Graph plan: CSR-by-destination (+ by-source and by-relation orderings used by backward).
@@ -176,8 +182,8 @@ int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int
 /* ACCUMULATES into d_ent[l][n_ent,d], d_rel[l][n_rel,d] (caller zeroes): gloss[l] * dloss[l]/d. */
 int jmac_transe_margin_bwd(const float* const* ent, const float* const* rel, int n_layers, int d,
                            const int64_t* h, const int64_t* r, const int64_t* t, int64_t M,
-                           int64_t B, float margin, const float* score, const float* gloss,
-                           float* const* d_ent, float* const* d_rel, void* stream);
+                           int64_t B, int64_t n_ent, int64_t n_rel, float margin, const float* score,
+                           const float* gloss, float* const* d_ent, float* const* d_rel, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pair cosine: cos[m] = <A[ia_m], B[ib_m]> / (max(|A[ia_m]|,1e-12) max(|B[ib_m]|,1e-12)), the
@@ -185,9 +191,10 @@ int jmac_transe_margin_bwd(const float* const* ent, const float* const* rel, int
  * 268-287).  Backward ACCUMULATES into dA, dB (caller zeroes).
  * ------------------------------------------------------------------------------------------ */
 int jmac_pair_cos_fwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib,
-                      int64_t M, float* cosv, void* stream);
+                      int64_t M, int64_t nA, int64_t nB, float* cosv, void* stream);
 int jmac_pair_cos_bwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib,
-                      int64_t M, const float* gcos, float* dA, float* dB, void* stream);
+                      int64_t M, int64_t nA, int64_t nB, const float* gcos, float* dA, float* dB,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Link prediction: JMAC.forward_linkpred (src/jmac_model.py:301-313) and the ranking loop of
@@ -198,12 +205,12 @@ int jmac_pair_cos_bwd(const float* A, const float* B, int d, const int64_t* ia, 
  * is filt_idx[filt_ptr[b] .. filt_ptr[b+1]) (NULL = raw setting); the target itself never counts.
  * ------------------------------------------------------------------------------------------ */
 int jmac_l1_dist(const float* const* ent, const float* const* rel, int n_layers, int d,
-                 const int64_t* e_idx, const int64_t* r_idx, int64_t B, int64_t N, int pred_head,
-                 float* dist, void* stream);
+                 const int64_t* e_idx, const int64_t* r_idx, int64_t B, int64_t N, int64_t n_rel,
+                 int pred_head, float* dist, void* stream);
 int jmac_l1_rank(const float* const* ent, const float* const* rel, int n_layers, int d,
                  const int64_t* e_idx, const int64_t* r_idx, const int64_t* t_idx, int64_t B,
-                 int64_t N, int pred_head, const int64_t* filt_ptr, const int64_t* filt_idx,
-                 int32_t* rank, void* stream);
+                 int64_t N, int64_t n_rel, int pred_head, const int64_t* filt_ptr,
+                 const int64_t* filt_idx, int32_t* rank, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Alignment scorer: similarity GEMM on the 5th-gen tensor cores with a streaming epilogue

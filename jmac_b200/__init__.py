@@ -4,4 +4,11 @@ from . import _lib  # noqa: F401
 from .model import JMAC, BaseModel, RelationAwareLayer, get_param  # noqa: F401
 from .validate import CompletionEvaluator  # noqa: F401
 
-__all__ = ["JMAC", "BaseModel", "RelationAwareLayer", "CompletionEvaluator", "get_param"]
+
+
+def check_errors():
+    """Synchronise the device and raise IndexError if any kernel met an out-of-range index (see _lib.raise_if_flagged)."""
+    _lib.raise_if_flagged(sync=True)
+
+
+__all__ = ["JMAC", "BaseModel", "RelationAwareLayer", "CompletionEvaluator", "get_param", "check_errors"]

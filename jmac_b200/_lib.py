@@ -18,6 +18,7 @@ _SIGNATURES = {
     "jmac_version": (c_char_p, []),
     "jmac_last_error": (c_char_p, []),
     "jmac_launch_count": (ctypes.c_uint64, []),
+    "jmac_status_poll": (c_int, []),
     "jmac_plan_create": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_create_bipartite": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_destroy": (c_int, [P]),
@@ -38,10 +39,10 @@ _SIGNATURES = {
     "jmac_gemm_tn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "jmac_gemm_tn_tf32x3": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, P, P]),
     "jmac_transe_margin_fwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P]),
-    "jmac_transe_margin_bwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_float, P, P, P, P, P]),
-    "jmac_pair_cos_fwd": (c_int, [P, P, c_int, P, P, c_int64, P, P]),
-    "jmac_pair_cos_bwd": (c_int, [P, P, c_int, P, P, c_int64, P, P, P, P]),
-    "jmac_l1_dist": (c_int, [P, P, c_int, c_int, P, P, c_int64, c_int64, c_int, P, P]),
+    "jmac_transe_margin_bwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, P, P]),
+    "jmac_pair_cos_fwd": (c_int, [P, P, c_int, P, P, c_int64, c_int64, c_int64, P, P]),
+    "jmac_pair_cos_bwd": (c_int, [P, P, c_int, P, P, c_int64, c_int64, c_int64, P, P, P, P]),
+    "jmac_l1_dist": (c_int, [P, P, c_int, c_int, P, P, c_int64, c_int64, c_int64, c_int, P, P]),
     "jmac_sm_count": (c_int, []),
     "jmac_sim_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "jmac_sim_grid": (c_int, [c_int64, c_int64, c_int]),
@@ -52,7 +53,7 @@ _SIGNATURES = {
     "jmac_csls_gold": (c_int, [c_float, P, P, P, P, c_int64, P, P]),
     "jmac_sim_softmax_stats": (c_int, [P, P, c_int64, c_int64, c_int, c_float, P, P, c_float, P, P, P, P, P, c_size_t, P]),
     "jmac_sim_softmax_stats_f32": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_float, P, P, c_float, P, P, P, P, P, c_size_t, P]),
-    "jmac_l1_rank": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int, P, P, P, P]),
+    "jmac_l1_rank": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int, P, P, P, P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -84,6 +85,26 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().jmac_last_error().decode(errors="replace")
         raise JmacError(f"{what or 'libjmac_b200'} failed with code {rc}: {msg}")
+
+
+_STATUS_WHAT = {0: "batch_h / batch_r / batch_t of the completion scorer", 1: "an index list of the pair-cosine (alignment) loss",
+                2: "e_index / r_index / target / filter list of link prediction"}
+
+
+def raise_if_flagged(sync: bool = False):
+    """IndexError if a kernel met an index outside its table since the last poll (the reference raises IndexError on the
+    CPU and a device-side assert on CUDA; here the kernel substitutes row 0, raises a flag in mapped host memory and
+    carries on, so nothing is read or written out of bounds).  Called without synchronising at the entry of every
+    index-consuming op -- an error surfaces at the next such call -- and with ``sync=True`` by ``jmac_b200.check_errors()``."""
+    lib = load()
+    if sync:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    bits = lib.jmac_status_poll()
+    if bits:
+        what = "; ".join(v for k, v in _STATUS_WHAT.items() if bits & (1 << k))
+        raise IndexError(f"index out of range in {what} (detected on the device)")
 
 
 def ptr(t):

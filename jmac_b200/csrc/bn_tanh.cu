@@ -157,7 +157,7 @@ extern "C" int jmac_bn_stats(const float* pre, int64_t N, int d, double* sums, v
     if (N == 0) return 0;
     dim3 block;
     stats_dims(d / 4, &block);
-    int64_t want = (N + block.y - 1) / block.y;
+    int64_t want = (N + block.y * 32 - 1) / (block.y * 32);          // >= 32 rows per thread: the double atomics at the end stay few
     int blocks = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
     col_stats_kernel<1><<<blocks, block, 0, (cudaStream_t)stream>>>(pre, nullptr, nullptr, nullptr, nullptr, N, d / 4, sums);
     JMAC_LAUNCH_CHECK();
@@ -185,7 +185,7 @@ extern "C" int jmac_bn_tanh_bwd_stats(const float* gout, const float* out, const
     if (N == 0) return 0;
     dim3 block;
     stats_dims(d / 4, &block);
-    int64_t want = (N + block.y - 1) / block.y;
+    int64_t want = (N + block.y * 32 - 1) / (block.y * 32);
     int blocks = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
     col_stats_kernel<3><<<blocks, block, 0, (cudaStream_t)stream>>>(gout, out, pre, mean, rstd, N, d / 4, bsums);
     JMAC_LAUNCH_CHECK();

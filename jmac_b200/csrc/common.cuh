@@ -11,6 +11,11 @@ namespace jmac {
 void set_error(const char* fmt, ...);
 int sm_count();
 void count_launch();
+// Device-visible status words in mapped, pinned host memory: kernels that consume caller-provided index lists store 1 into
+// word `which` when an index is out of range (and use row 0 instead, so nothing is read or written out of bounds);
+// jmac_status_poll() reads and clears them without synchronising anything.  nullptr if the allocation failed.
+int* status_words();
+enum { JMAC_ST_TRIPLE = 0, JMAC_ST_PAIR = 1, JMAC_ST_LINKPRED = 2, JMAC_ST_WORDS = 8 };
 
 #define JMAC_CUDA(expr)                                                                    \
     do {                                                                                   \
@@ -105,6 +110,15 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
 // vector reduction (no return) -- sm_90+: one 16-byte RED instead of four.
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// an index taken from the caller: flagged and replaced by 0 when it is outside [0, n)
+__device__ __forceinline__ int64_t safe_index(int64_t v, int64_t n, int* status_word) {
+    if ((uint64_t)v >= (uint64_t)n) {
+        if (status_word) *reinterpret_cast<volatile int*>(status_word) = 1;
+        return 0;
+    }
+    return v;
 }
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }

@@ -93,7 +93,7 @@ struct GemmParams {
     int ldc;
     const float *D1, *D2;   // optional [M,N] addends of the epilogue (C = A.B^T + D1 + D2), leading dimension ldd; may alias C
     int ldd;
-    int exact_lo;           // != 0: the lo terms are rounded to TF32 (nothing left for the tensor core to truncate) and lo.lo is added
+    int nsplit, Nc;         // small M: every 256-row block is shared by nsplit CTAs, each computing Nc = N / nsplit output columns
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -107,7 +107,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t tma_full0 = bars, xf_full0 = bars + 8 * G_NS, empty0 = bars + 16 * G_NS, acc_full = bars + 24 * G_NS,
                    acc_empty = acc_full + 8, tmem_slot = acc_empty + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_mb = (p.M + G_BM - 1) / G_BM;
+    const int n_units = ((p.M + G_BM - 1) / G_BM) * p.nsplit;       // unit u = (row block u / nsplit, column part u % nsplit)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_NS; ++s) { mbar_init(tma_full0 + 8 * s, 1); mbar_init(xf_full0 + 8 * s, 8); mbar_init(empty0 + 8 * s, 1); }
@@ -124,29 +124,30 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    const uint32_t b_bytes = (uint32_t)p.N * G_BK * 4;
+    const uint32_t b_bytes = (uint32_t)p.Nc * G_BK * 4;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int mb = blockIdx.x; mb < n_mb; mb += gridDim.x) {
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int mb = u / p.nsplit, n0 = (u % p.nsplit) * p.Nc;
                 for (int kb = 0; kb < p.nkb; ++kb, ++it) {
                     const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
                     const uint32_t st = base + s * G_STAGE;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     mbar_expect_tx(tma_full0 + 8 * s, G_A_BYTES + 2 * b_bytes);
                     tma_load_2d(st, &map_a, tma_full0 + 8 * s, kb * G_BK, mb * G_BM);
-                    tma_load_2d(st + 2 * G_A_BYTES, &map_bhi, tma_full0 + 8 * s, kb * G_BK, 0);
-                    tma_load_2d(st + 2 * G_A_BYTES + G_B_BYTES, &map_blo, tma_full0 + 8 * s, kb * G_BK, 0);
+                    tma_load_2d(st + 2 * G_A_BYTES, &map_bhi, tma_full0 + 8 * s, kb * G_BK, n0);
+                    tma_load_2d(st + 2 * G_A_BYTES + G_B_BYTES, &map_blo, tma_full0 + 8 * s, kb * G_BK, n0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // kind::tf32: A = B = TF32 (2), D = F32 (1), K-major both, M = 128, N = p.N
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t it = 0, tcount = 0;
-            for (int mb = blockIdx.x; mb < n_mb; mb += gridDim.x, ++tcount) {
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++tcount) {
                 mbar_wait(acc_empty, (tcount & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < p.nkb; ++kb, ++it) {
@@ -166,7 +167,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             tc_mma_tf32(d_tmem, ahi + o, bhi + o, idesc, (kb | kk) != 0 ? 1u : 0u);
                             tc_mma_tf32(d_tmem, alo + o, bhi + o, idesc, 1u);
                             tc_mma_tf32(d_tmem, ahi + o, blo + o, idesc, 1u);
-                            if (p.exact_lo & 2) tc_mma_tf32(d_tmem, alo + o, blo + o, idesc, 1u);
                         }
                     }
                     tc_commit(empty0 + 8 * s);
@@ -178,7 +178,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int w = warp - 2;                       // 0..7
         const int quarter = warp & 3, half = w >> 2;
         uint32_t it = 0, tcount = 0;
-        for (int mb = blockIdx.x; mb < n_mb; mb += gridDim.x, ++tcount) {
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++tcount) {
+            const int mb = u / p.nsplit, n0 = (u % p.nsplit) * p.Nc;
             // ---- split the A slices of this block as they land
             for (int kb = 0; kb < p.nkb; ++kb, ++it) {
                 const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
@@ -194,7 +195,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     h.y = tf32_rna(x.y); l.y = x.y - h.y;
                     h.z = tf32_rna(x.z); l.z = x.z - h.z;
                     h.w = tf32_rna(x.w); l.w = x.w - h.w;
-                    if (p.exact_lo & 1) { l.x = tf32_rna(l.x); l.y = tf32_rna(l.y); l.z = tf32_rna(l.z); l.w = tf32_rna(l.w); }
                     hi[i] = h;
                     lo[i] = l;
                 }
@@ -207,11 +207,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tc_fence_after();
             const int row = mb * G_BM + half * 128 + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 256;
-            float* crow = p.C + (size_t)row * p.ldc;
-            const float* d1row = p.D1 ? p.D1 + (size_t)row * p.ldd : nullptr;
-            const float* d2row = p.D2 ? p.D2 + (size_t)row * p.ldd : nullptr;
+            float* crow = p.C + (size_t)row * p.ldc + n0;
+            const float* d1row = p.D1 ? p.D1 + (size_t)row * p.ldd + n0 : nullptr;
+            const float* d2row = p.D2 ? p.D2 + (size_t)row * p.ldd + n0 : nullptr;
             uint32_t raw[2][32];
-            const int nchunk = p.N / 32;               // N % 32 == 0 enforced by the host
+            const int nchunk = p.Nc / 32;              // Nc % 32 == 0 enforced by the host
             tc_ld32_issue(taddr, raw[0]);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -442,15 +442,28 @@ gemm_tf32x3_tn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-__global__ void sum_partials_f32_kernel(const float* __restrict__ partial, int n_part, int64_t n4, float* __restrict__ out) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n4) return;
+// out = sum over the n_part per-CTA partials, in a fixed order (deterministic).  256 threads = 32 outputs (float4) x 8 groups:
+// group g adds partials g, g + 8, ... (independent, coalesced 512-byte loads), the groups are then combined in order 0..7.
+__global__ void __launch_bounds__(256) sum_partials_f32_kernel(const float* __restrict__ partial, int n_part, int64_t n4, float* __restrict__ out) {
+    __shared__ float4 sh[8][32];
+    const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + o;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < n_part; ++k) {
-        const float4 v = reinterpret_cast<const float4*>(partial)[(size_t)k * n4 + i];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (i < n4) {
+#pragma unroll 4
+        for (int k = g; k < n_part; k += 8) {
+            const float4 v = reinterpret_cast<const float4*>(partial)[(size_t)k * n4 + i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
+    sh[g][o] = acc;
+    __syncthreads();
+    if (g == 0 && i < n4) {
+        float4 t = sh[0][o];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) { t.x += sh[q][o].x; t.y += sh[q][o].y; t.z += sh[q][o].z; t.w += sh[q][o].w; }
+        reinterpret_cast<float4*>(out)[i] = t;
+    }
 }
 
 int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int feat, int64_t ld) {
@@ -496,7 +509,7 @@ extern "C" int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, 
     gemm_tf32x3_tn_kernel<<<grid, G_THREADS, T_SMEM, st>>>(map_x, map_g, p);
     JMAC_LAUNCH_CHECK();
     const int64_t n4 = (int64_t)KO * N / 4;
-    sum_partials_f32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(workspace, grid, n4, D);
+    sum_partials_f32_kernel<<<(unsigned)((n4 + 31) / 32), 256, 0, st>>>(workspace, grid, n4, D);
     JMAC_LAUNCH_CHECK();
     return 0;
 }
@@ -514,20 +527,26 @@ extern "C" int jmac_gemm_tf32x3_add(const float* A, int64_t lda, const float* B_
     JMAC_ARG(N >= 32 && N <= 256 && (N % 32) == 0 && K >= 16 && (K % 16) == 0);
     JMAC_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 8) == 0);      // C, D: 256-bit row accesses
     JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)B_lo % 16) == 0 && ((uintptr_t)C % 32) == 0);
+    // few row blocks (the reference's graph sizes: 5-14 k nodes = 20-55 blocks of 256 rows): share every block among 2 or 4
+    // CTAs, each computing N/2 or N/4 output columns, so that the launch covers the machine
+    const int n_mb = (int)((M + G_BM - 1) / G_BM);
+    int nsplit = 1;
+    if (n_mb * 4 <= sm_count() && (N % 128) == 0) nsplit = 4;
+    else if (n_mb * 2 <= sm_count() && (N % 64) == 0) nsplit = 2;
+    const int Nc = N / nsplit;
     CUtensorMap map_a, map_bhi, map_blo;
     int rc = make_map_f32(&map_a, A, M, K, lda, G_BM);
     if (rc) return rc;
-    rc = make_map_f32(&map_bhi, B_hi, N, K, ldb, N);
+    rc = make_map_f32(&map_bhi, B_hi, N, K, ldb, Nc);
     if (rc) return rc;
-    rc = make_map_f32(&map_blo, B_lo, N, K, ldb, N);
+    rc = make_map_f32(&map_blo, B_lo, N, K, ldb, Nc);
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = N; p.nkb = K / G_BK; p.C = C; p.ldc = (int)ldc;
     p.D1 = D1; p.D2 = D2; p.ldd = (int)ldd;
-    static const int gemm_mode = getenv("JMAC_GEMM_MODE") ? atoi(getenv("JMAC_GEMM_MODE")) : 0;
-    p.exact_lo = gemm_mode;
-    const int n_mb = (int)((M + G_BM - 1) / G_BM);
-    const int grid = n_mb < sm_count() ? n_mb : sm_count();
+    p.nsplit = nsplit; p.Nc = Nc;
+    const int n_units = n_mb * nsplit;
+    const int grid = n_units < sm_count() ? n_units : sm_count();
     JMAC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     gemm_tf32x3_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(map_a, map_bhi, map_blo, p);
     JMAC_LAUNCH_CHECK();

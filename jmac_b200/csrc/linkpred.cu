@@ -22,7 +22,8 @@ struct L1Params {
     const float* rel[LP_MAX_LAYERS];
     int n_layers, d;
     const int64_t *e_idx, *r_idx, *t_idx;
-    int64_t B, N;
+    int64_t B, N, n_rel;
+    int* status;          // out-of-range index flag
     float sign;
     float* dist;          // [B,N] or null
     const float* tdist;   // [B] or null
@@ -49,7 +50,7 @@ __device__ __forceinline__ float l1_seq(const L1Params& p, int64_t e, int64_t r,
 __global__ void l1_target_kernel(L1Params p, float* __restrict__ tdist, int* __restrict__ rank) {
     const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= p.B) return;
-    tdist[b] = l1_seq(p, p.e_idx[b], p.r_idx[b], p.t_idx[b]);
+    tdist[b] = l1_seq(p, safe_index(p.e_idx[b], p.N, p.status), safe_index(p.r_idx[b], p.n_rel, p.status), safe_index(p.t_idx[b], p.N, p.status));
     rank[b] = 1;
 }
 
@@ -59,11 +60,11 @@ __global__ void l1_filter_kernel(L1Params p, const int64_t* __restrict__ filt_pt
     const int lane = threadIdx.x & 31;
     const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (b >= p.B) return;
-    const int64_t e = p.e_idx[b], r = p.r_idx[b], t = p.t_idx[b];
+    const int64_t e = safe_index(p.e_idx[b], p.N, p.status), r = safe_index(p.r_idx[b], p.n_rel, p.status), t = safe_index(p.t_idx[b], p.N, p.status);
     const float td = tdist[b];
     int cnt = 0;
     for (int64_t f = filt_ptr[b] + lane; f < filt_ptr[b + 1]; f += 32) {
-        const int64_t n = filt_idx[f];
+        const int64_t n = safe_index(filt_idx[f], p.N, p.status);
         if (n == t || n < 0 || n >= p.N) continue;
         if (l1_seq(p, e, r, n) < td) ++cnt;
     }
@@ -103,8 +104,8 @@ __global__ void __launch_bounds__(256) l1_tile_kernel(L1Params p) {
                 float4 qv = f4_zero(), cv = f4_zero();
                 if (kk < p.d) {
                     if (q0 + row < p.B) {
-                        const float4 ev = __ldg(reinterpret_cast<const float4*>(ent + p.e_idx[q0 + row] * p.d + kk));
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rel + p.r_idx[q0 + row] * p.d + kk));
+                        const float4 ev = __ldg(reinterpret_cast<const float4*>(ent + safe_index(p.e_idx[q0 + row], p.N, p.status) * p.d + kk));
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rel + safe_index(p.r_idx[q0 + row], p.n_rel, p.status) * p.d + kk));
                         qv = make_float4(__fadd_rn(ev.x, p.sign * rv.x), __fadd_rn(ev.y, p.sign * rv.y), __fadd_rn(ev.z, p.sign * rv.z),
                                          __fadd_rn(ev.w, p.sign * rv.w));
                     }
@@ -173,9 +174,11 @@ __global__ void __launch_bounds__(256) l1_tile_kernel(L1Params p) {
 using namespace jmac;
 
 static int fill_l1(L1Params& p, const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* e_idx,
-                   const int64_t* r_idx, int64_t B, int64_t N, int pred_head) {
+                   const int64_t* r_idx, int64_t B, int64_t N, int64_t n_rel, int pred_head) {
     JMAC_ARG(ent && rel && e_idx && r_idx);
-    JMAC_ARG(n_layers >= 1 && n_layers <= LP_MAX_LAYERS && d >= 4 && (d % 4) == 0 && B > 0 && N > 0);
+    JMAC_ARG(n_layers >= 1 && n_layers <= LP_MAX_LAYERS && d >= 4 && (d % 4) == 0 && B > 0 && N > 0 && n_rel > 0);
+    p.n_rel = n_rel;
+    p.status = status_words() ? status_words() + JMAC_ST_LINKPRED : nullptr;
     for (int l = 0; l < LP_MAX_LAYERS; ++l) p.ent[l] = p.rel[l] = nullptr;
     for (int l = 0; l < n_layers; ++l) {
         JMAC_ARG(ent[l] && rel[l]);
@@ -188,9 +191,9 @@ static int fill_l1(L1Params& p, const float* const* ent, const float* const* rel
 }
 
 extern "C" int jmac_l1_dist(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* e_idx,
-                            const int64_t* r_idx, int64_t B, int64_t N, int pred_head, float* dist, void* stream) {
+                            const int64_t* r_idx, int64_t B, int64_t N, int64_t n_rel, int pred_head, float* dist, void* stream) {
     L1Params p;
-    int rc = fill_l1(p, ent, rel, n_layers, d, e_idx, r_idx, B, N, pred_head);
+    int rc = fill_l1(p, ent, rel, n_layers, d, e_idx, r_idx, B, N, n_rel, pred_head);
     if (rc) return rc;
     JMAC_ARG(dist != nullptr);
     p.dist = dist;
@@ -201,10 +204,10 @@ extern "C" int jmac_l1_dist(const float* const* ent, const float* const* rel, in
 }
 
 extern "C" int jmac_l1_rank(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* e_idx,
-                            const int64_t* r_idx, const int64_t* t_idx, int64_t B, int64_t N, int pred_head, const int64_t* filt_ptr,
-                            const int64_t* filt_idx, int32_t* rank, void* stream) {
+                            const int64_t* r_idx, const int64_t* t_idx, int64_t B, int64_t N, int64_t n_rel, int pred_head,
+                            const int64_t* filt_ptr, const int64_t* filt_idx, int32_t* rank, void* stream) {
     L1Params p;
-    int rc = fill_l1(p, ent, rel, n_layers, d, e_idx, r_idx, B, N, pred_head);
+    int rc = fill_l1(p, ent, rel, n_layers, d, e_idx, r_idx, B, N, n_rel, pred_head);
     if (rc) return rc;
     JMAC_ARG(t_idx && rank);
     JMAC_ARG((filt_ptr == nullptr) == (filt_idx == nullptr) || filt_ptr != nullptr);

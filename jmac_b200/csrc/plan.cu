@@ -24,6 +24,22 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int* status_words() {
+    static int* host = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* q = nullptr;
+        if (cudaHostAlloc(&q, sizeof(int) * JMAC_ST_WORDS, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+            host = static_cast<int*>(q);
+            for (int i = 0; i < JMAC_ST_WORDS; ++i) host[i] = 0;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    return host;      // unified addressing: the same pointer is valid on every device
+}
+
 int sm_count() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -236,6 +252,16 @@ extern "C" const char* jmac_version(void) { return "jmac_b200 0.1 (sm_100a)"; }
 extern "C" const char* jmac_last_error(void) { return jmac::g_err; }
 extern "C" uint64_t jmac_launch_count(void) { return __atomic_load_n(&jmac::g_launches, __ATOMIC_RELAXED); }
 
+extern "C" int jmac_status_poll(void) {
+    int* w = jmac::status_words();
+    int bits = 0;
+    if (w) {
+        for (int i = 0; i < jmac::JMAC_ST_WORDS; ++i)
+            if (__atomic_exchange_n(&w[i], 0, __ATOMIC_RELAXED)) bits |= 1 << i;
+    }
+    return bits;
+}
+
 extern "C" int jmac_plan_destroy(jmac_plan* p) {
     if (!p) return 0;
     // One device-wide wait (any stream may still be reading the plan), then stream-ordered frees back into the pool:
@@ -350,7 +376,15 @@ extern "C" int jmac_plan_create_bipartite(const int64_t* d_row, const int64_t* d
     jmac_plan* p = new (std::nothrow) jmac_plan();
     if (!p) return JMAC_ENOMEM;
     p->E = E; p->N = N_dst; p->N_src = N_src; p->n_rel = n_rel;
-    p->chunk = chunk > 0 ? chunk : 256;
+    // Work-item size: 256 edges on large graphs; on the reference's graph sizes (1e4-1e5 edges) a warp's fair share of the
+    // edges is a few dozen, and a 256-edge slice of a hub would be 8x that -- the whole launch would wait for the hub warps.
+    if (chunk > 0) p->chunk = chunk;
+    else {
+        const int64_t per = E / ((int64_t)sm_count() * RING_WARPS);
+        int c = 32;
+        while (c < 256 && c < per) c <<= 1;
+        p->chunk = c;
+    }
     if (cudaGetDevice(&p->device) != cudaSuccess) p->device = 0;
     int rc = plan_build(p, d_row, d_col, d_type, (cudaStream_t)stream);
     if (rc == 0 && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = JMAC_EINVAL;   // complete on return: usable from any stream

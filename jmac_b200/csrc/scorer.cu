@@ -30,6 +30,8 @@ struct TransEParams {
     float* score;        // [n_layers, M]
     float* loss;         // [n_layers]
     const float* gloss;  // [n_layers]
+    int64_t n_ent, n_rel;
+    int* status;         // out-of-range index flag (common.cuh: status_words)
 };
 
 __global__ void fill_kernel(float* p, int n, float v) {
@@ -68,7 +70,9 @@ __global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
                 int hv = 0, rv = 0, tv = 0;
                 if (lane < cnt) {
                     const int64_t m = (int64_t)(kb + lane) * p.B + b;
-                    hv = (int)__ldg(p.h + m); rv = (int)__ldg(p.r + m); tv = (int)__ldg(p.t + m);
+                    hv = (int)safe_index(__ldg(p.h + m), p.n_ent, p.status);
+                    rv = (int)safe_index(__ldg(p.r + m), p.n_rel, p.status);
+                    tv = (int)safe_index(__ldg(p.t + m), p.n_ent, p.status);
                 }
                 float sc_keep = 0.f;
                 for (int k = 0; k < cnt; k += U) {
@@ -152,7 +156,8 @@ __global__ void __launch_bounds__(256) transe_bwd_kernel(TransEParams p) {
             if (k == 0) ds = gs * (float)act;
             else ds = (pos - score[m] > -p.margin) ? -gs : 0.f;
             if (ds == 0.f) continue;  // warp-uniform: inactive negatives cost no row traffic
-            const int64_t hh = __ldg(p.h + m), rr = __ldg(p.r + m), tt = __ldg(p.t + m);
+            const int64_t hh = safe_index(__ldg(p.h + m), p.n_ent, p.status), rr = safe_index(__ldg(p.r + m), p.n_rel, p.status),
+                          tt = safe_index(__ldg(p.t + m), p.n_ent, p.status);
             Row<VPL> tr;
             load_row<VPL, true>(tr, ent, tt, d4, lane);
             if (hh != hprev || rr != rprev) {
@@ -190,13 +195,13 @@ __global__ void __launch_bounds__(256) transe_bwd_kernel(TransEParams p) {
 template <int VPL>
 __global__ void __launch_bounds__(256) pair_cos_fwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int d4,
                                                            const int64_t* __restrict__ ia, const int64_t* __restrict__ ib, int64_t M,
-                                                           float* __restrict__ cosv) {
+                                                           int64_t nA, int64_t nB, int* status, float* __restrict__ cosv) {
     const int lane = threadIdx.x & 31;
     const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
     Row<VPL> a, b;
-    load_row<VPL, true>(a, A, ia[m], d4, lane);
-    load_row<VPL, true>(b, Bm, ib[m], d4, lane);
+    load_row<VPL, true>(a, A, safe_index(ia[m], nA, status), d4, lane);
+    load_row<VPL, true>(b, Bm, safe_index(ib[m], nB, status), d4, lane);
     float dt = 0.f, na = 0.f, nb = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) { dt += dot4(a.v[i], b.v[i]); na += dot4(a.v[i], a.v[i]); nb += dot4(b.v[i], b.v[i]); }
@@ -210,13 +215,14 @@ __global__ void __launch_bounds__(256) pair_cos_fwd_kernel(const float* __restri
 template <int VPL>
 __global__ void __launch_bounds__(256) pair_cos_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int d4,
                                                            const int64_t* __restrict__ ia, const int64_t* __restrict__ ib, int64_t M,
-                                                           const float* __restrict__ gcos, float* __restrict__ dA, float* __restrict__ dB) {
+                                                           int64_t nA, int64_t nB, int* status, const float* __restrict__ gcos,
+                                                           float* __restrict__ dA, float* __restrict__ dB) {
     const int lane = threadIdx.x & 31;
     const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
     const float g = gcos[m];
     if (g == 0.f) return;  // hinge-inactive pair
-    const int64_t ra = ia[m], rb = ib[m];
+    const int64_t ra = safe_index(ia[m], nA, status), rb = safe_index(ib[m], nB, status);
     Row<VPL> a, b;
     load_row<VPL, true>(a, A, ra, d4, lane);
     load_row<VPL, true>(b, Bm, rb, d4, lane);
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(256) pair_cos_bwd_kernel(const float* __restri
 using namespace jmac;
 
 static int fill_transe(TransEParams& p, const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
-                       const int64_t* r, const int64_t* t, int64_t M, int64_t B, float margin) {
+                       const int64_t* r, const int64_t* t, int64_t M, int64_t B, int64_t n_ent, int64_t n_rel, float margin) {
     JMAC_ARG(ent && rel && h && r && t);
     JMAC_ARG(n_layers >= 1 && n_layers <= MAX_LAYERS && dim_ok(d));
     JMAC_ARG(B > 0 && M >= 2 * B && (M % B) == 0 && M / B < (1 << 20));
@@ -260,15 +266,16 @@ static int fill_transe(TransEParams& p, const float* const* ent, const float* co
     }
     p.n_layers = n_layers; p.d4 = d / 4; p.h = h; p.r = r; p.t = t; p.M = M; p.B = B; p.K1 = (int)(M / B); p.margin = margin;
     p.score = nullptr; p.loss = nullptr; p.gloss = nullptr;
+    JMAC_ARG(n_ent > 0 && n_ent < (int64_t(1) << 31) && n_rel > 0 && n_rel < (int64_t(1) << 31));      // the kernels keep ids in 32 bits
+    p.n_ent = n_ent; p.n_rel = n_rel; p.status = status_words() ? status_words() + JMAC_ST_TRIPLE : nullptr;
     return 0;
 }
 
 extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
                                       const int64_t* r, const int64_t* t, int64_t M, int64_t B, int64_t n_ent, int64_t n_rel,
                                       float margin, float* score, float* loss, void* stream) {
-    JMAC_ARG(n_ent > 0 && n_ent < (int64_t(1) << 31) && n_rel > 0 && n_rel < (int64_t(1) << 31));      // the kernels keep ids in 32 bits
     TransEParams p;
-    int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, margin);
+    int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, n_ent, n_rel, margin);
     if (rc) return rc;
     JMAC_ARG(score && loss);
     p.score = score; p.loss = loss;
@@ -286,10 +293,10 @@ extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* cons
 }
 
 extern "C" int jmac_transe_margin_bwd(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
-                                      const int64_t* r, const int64_t* t, int64_t M, int64_t B, float margin, const float* score,
-                                      const float* gloss, float* const* d_ent, float* const* d_rel, void* stream) {
+                                      const int64_t* r, const int64_t* t, int64_t M, int64_t B, int64_t n_ent, int64_t n_rel, float margin,
+                                      const float* score, const float* gloss, float* const* d_ent, float* const* d_rel, void* stream) {
     TransEParams p;
-    int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, margin);
+    int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, n_ent, n_rel, margin);
     if (rc) return rc;
     JMAC_ARG(score && gloss && d_ent && d_rel);
     for (int l = 0; l < n_layers; ++l) {
@@ -304,24 +311,26 @@ extern "C" int jmac_transe_margin_bwd(const float* const* ent, const float* cons
     return 0;
 }
 
-extern "C" int jmac_pair_cos_fwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib, int64_t M, float* cosv,
-                                 void* stream) {
-    JMAC_ARG(A && B && dim_ok(d) && M >= 0);
+extern "C" int jmac_pair_cos_fwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib, int64_t M, int64_t nA,
+                                 int64_t nB, float* cosv, void* stream) {
+    JMAC_ARG(A && B && dim_ok(d) && M >= 0 && nA > 0 && nB > 0);
     if (M == 0) return 0;
     JMAC_ARG(ia && ib && cosv);
     const int64_t blocks = (M + 7) / 8;
-    JMAC_DISPATCH_VPL(d, { pair_cos_fwd_kernel<VPL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d / 4, ia, ib, M, cosv); });
+    int* status = status_words() ? status_words() + JMAC_ST_PAIR : nullptr;
+    JMAC_DISPATCH_VPL(d, { pair_cos_fwd_kernel<VPL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d / 4, ia, ib, M, nA, nB, status, cosv); });
     JMAC_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int jmac_pair_cos_bwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib, int64_t M,
-                                 const float* gcos, float* dA, float* dB, void* stream) {
-    JMAC_ARG(A && B && dim_ok(d) && M >= 0);
+extern "C" int jmac_pair_cos_bwd(const float* A, const float* B, int d, const int64_t* ia, const int64_t* ib, int64_t M, int64_t nA,
+                                 int64_t nB, const float* gcos, float* dA, float* dB, void* stream) {
+    JMAC_ARG(A && B && dim_ok(d) && M >= 0 && nA > 0 && nB > 0);
     if (M == 0) return 0;
     JMAC_ARG(ia && ib && gcos && dA && dB);
     const int64_t blocks = (M + 7) / 8;
-    JMAC_DISPATCH_VPL(d, { pair_cos_bwd_kernel<VPL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d / 4, ia, ib, M, gcos, dA, dB); });
+    int* status = status_words() ? status_words() + JMAC_ST_PAIR : nullptr;
+    JMAC_DISPATCH_VPL(d, { pair_cos_bwd_kernel<VPL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d / 4, ia, ib, M, nA, nB, status, gcos, dA, dB); });
     JMAC_LAUNCH_CHECK();
     return 0;
 }

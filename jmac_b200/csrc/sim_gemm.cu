@@ -394,13 +394,18 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             st_m = cmax;
                             st_arg = col0 + carg;
                         }
+                        // the 32 terms of the chunk are summed on their own first: adding thousands of tiny terms one by one to a
+                        // Z ~ 1 dominated by the gold column would round each of them to ulp(1)
+                        float cz = 0.f, cw = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float t = ok[j] ? v[j] - st_m : 0.f;
                             const float e = ok[j] ? __expf(t) : 0.f;
-                            st_Z += e;
-                            st_W = fmaf(e, t, st_W);
+                            cz += e;
+                            cw = fmaf(e, t, cw);
                         }
+                        st_Z += cz;
+                        st_W += cw;
                         continue;
                     }
                     if (CSLS) {

@@ -302,18 +302,11 @@ def attn_edge(plan, X, W_att, Rp, a_att, slope, X_src=None):
 # ----------------------------------------------------------------------------------------------
 # node-level dense products (3xTF32 on tcgen05, fp32-accurate)
 # ----------------------------------------------------------------------------------------------
-import os as _os
-_GEMM_MODE = int(_os.environ.get("JMAC_GEMM_MODE", "0"))
-
-
 def _split_tf32(w_nk: torch.Tensor):
     """hi = w rounded to nearest TF32 (ties away, like cvt.rna.tf32.f32; low 13 mantissa bits zero),
     lo = w - hi (exact in fp32)."""
     hi = ((w_nk.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
-    lo = w_nk - hi
-    if _GEMM_MODE & 1:          # lo rounded to TF32 as well: nothing is left for the tensor core to truncate
-        lo = ((lo.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
-    return hi, lo
+    return hi, w_nk - hi
 
 
 def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
@@ -488,6 +481,7 @@ class TransEMarginFn(torch.autograd.Function):
         if M % B != 0 or M // B < 2:
             # same failure the reference hits in score.view(-1, batch_size) (src/jmac_model.py:358,367)
             raise RuntimeError(f"shape '[-1, {B}]' is invalid for input of size {M - B}")
+        _lib.raise_if_flagged()
         score = torch.empty(n_layers * M, dtype=torch.float32, device=dev)
         loss = torch.empty(n_layers, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -510,7 +504,8 @@ class TransEMarginFn(torch.autograd.Function):
         d_ents = [torch.zeros_like(x) for x in ents]
         d_rels = [torch.zeros_like(x) for x in rels]
         with torch.cuda.device(dev):
-            check(lib.jmac_transe_margin_bwd(_ptr_array(ents), _ptr_array(rels), n_layers, d, ptr(h), ptr(r), ptr(t), M, B, margin,
+            check(lib.jmac_transe_margin_bwd(_ptr_array(ents), _ptr_array(rels), n_layers, d, ptr(h), ptr(r), ptr(t), M, B,
+                                             ents[0].shape[0], rels[0].shape[0], margin,
                                              ptr(score), ptr(gloss), _ptr_array(d_ents), _ptr_array(d_rels), stream_ptr()),
                   "jmac_transe_margin_bwd")
         return (None, None, None, None, None, *d_ents, *d_rels)
@@ -530,9 +525,11 @@ class PairCosFn(torch.autograd.Function):
         dev = A.device
         ia, ib = as_index(ia, dev).reshape(-1), as_index(ib, dev).reshape(-1)
         M = int(ia.numel())
+        _lib.raise_if_flagged()
         cosv = torch.empty(M, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.jmac_pair_cos_fwd(ptr(A), ptr(B), A.shape[1], ptr(ia), ptr(ib), M, ptr(cosv), stream_ptr()), "jmac_pair_cos_fwd")
+            check(lib.jmac_pair_cos_fwd(ptr(A), ptr(B), A.shape[1], ptr(ia), ptr(ib), M, A.shape[0], B.shape[0], ptr(cosv), stream_ptr()),
+                  "jmac_pair_cos_fwd")
         ctx.save_for_backward(A, B, ia, ib)
         return cosv
 
@@ -544,7 +541,8 @@ class PairCosFn(torch.autograd.Function):
         dA = torch.zeros_like(A)
         dB = torch.zeros_like(B)
         with torch.cuda.device(A.device):
-            check(lib.jmac_pair_cos_bwd(ptr(A), ptr(B), A.shape[1], ptr(ia), ptr(ib), int(ia.numel()), ptr(g), ptr(dA), ptr(dB), stream_ptr()),
+            check(lib.jmac_pair_cos_bwd(ptr(A), ptr(B), A.shape[1], ptr(ia), ptr(ib), int(ia.numel()), A.shape[0], B.shape[0], ptr(g), ptr(dA),
+                                        ptr(dB), stream_ptr()),
                   "jmac_pair_cos_bwd")
         return dA, dB, None, None
 
@@ -567,9 +565,10 @@ def l1_dist(ents, rels, e_idx, r_idx, pred_head=False) -> torch.Tensor:
     dist = torch.empty(Bq, N, dtype=torch.float32, device=dev)
     if Bq == 0:
         return dist
+    _lib.raise_if_flagged()
     with torch.cuda.device(dev):
-        check(lib.jmac_l1_dist(_ptr_array(ents), _ptr_array(rels), len(ents), d, ptr(e_idx), ptr(r_idx), Bq, N, int(pred_head), ptr(dist),
-                               stream_ptr()), "jmac_l1_dist")
+        check(lib.jmac_l1_dist(_ptr_array(ents), _ptr_array(rels), len(ents), d, ptr(e_idx), ptr(r_idx), Bq, N, rels[0].shape[0], int(pred_head),
+                               ptr(dist), stream_ptr()), "jmac_l1_dist")
     return dist
 
 
@@ -587,7 +586,8 @@ def l1_rank(ents, rels, e_idx, r_idx, t_idx, filt_ptr=None, filt_idx=None, pred_
         return rank
     if filt_ptr is not None:
         filt_ptr, filt_idx = as_index(filt_ptr, dev), as_index(filt_idx, dev)
+    _lib.raise_if_flagged()
     with torch.cuda.device(dev):
-        check(lib.jmac_l1_rank(_ptr_array(ents), _ptr_array(rels), len(ents), d, ptr(e_idx), ptr(r_idx), ptr(t_idx), Bq, N, int(pred_head),
-                               ptr(filt_ptr), ptr(filt_idx), ptr(rank), stream_ptr()), "jmac_l1_rank")
+        check(lib.jmac_l1_rank(_ptr_array(ents), _ptr_array(rels), len(ents), d, ptr(e_idx), ptr(r_idx), ptr(t_idx), Bq, N, rels[0].shape[0],
+                               int(pred_head), ptr(filt_ptr), ptr(filt_idx), ptr(rank), stream_ptr()), "jmac_l1_rank")
     return rank

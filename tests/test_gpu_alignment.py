@@ -103,8 +103,8 @@ def test_split_launch_is_bit_identical_to_unsplit(n1, n2, d, k, prec):
     s = F.softmax_stats(A, B, 20.0, row_mask=mask1, col_mask=mask2, split=True)
     u = F.softmax_stats(A, B, 20.0, row_mask=mask1, col_mask=mask2, split=False)
     assert torch.equal(s["max"], u["max"]) and torch.equal(s["arg"], u["arg"])
-    torch.testing.assert_close(s["Z"], u["Z"], rtol=2e-5, atol=0)          # re-associated sums
-    torch.testing.assert_close(s["W"], u["W"], rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(s["Z"], u["Z"], rtol=1e-4, atol=0)          # re-associated fp32 sums of up to 30 000 terms
+    torch.testing.assert_close(s["W"], u["W"], rtol=2e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

@@ -11,7 +11,8 @@ def relerr(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max())
 
 
-@pytest.mark.parametrize("M,K,N", [(5000, 256, 256), (4097, 64, 128), (300, 256, 32), (70000, 256, 256), (1000, 16, 96), (257, 128, 224)])
+@pytest.mark.parametrize("M,K,N", [(5000, 256, 256), (4097, 64, 128), (300, 256, 32), (70000, 256, 256), (1000, 16, 96), (257, 128, 224),
+                                   (14000, 256, 256), (13176, 256, 192)])      # DBP-5L node counts: row blocks shared by 2 CTAs (N / 2 columns each)
 def test_gemm_tf32x3_matches_fp64(M, K, N):
     from jmac_b200 import functional as JF
     torch.manual_seed(M + N)
@@ -58,7 +59,7 @@ def test_node_mm_autograd_matches_torch():
     assert torch.equal(JF.node_mm(x2, w2), torch.mm(x2, w2))
 
 
-@pytest.mark.parametrize("M,K,N", [(5000, 256, 256), (4321, 128, 96), (513, 64, 32)])
+@pytest.mark.parametrize("M,K,N", [(5000, 256, 256), (4321, 128, 96), (513, 64, 32), (14000, 256, 256)])
 def test_gemm_epilogue_addends_and_in_place_accumulate(M, K, N):
     """jmac_gemm_tf32x3_add: C = A B^T + D1 + D2 with 256-bit epilogue accesses; D1 may alias C (gradient accumulation)."""
     from jmac_b200 import functional as JF

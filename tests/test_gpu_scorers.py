@@ -365,3 +365,95 @@ def test_negative_sampler_on_device_feeds_the_scorer():
                                  torch.cat((batch[:, 2], neg.t().reshape(-1))), B, 5.0)      # negatives [K, B] flattened: position B + k*B + b
     loss.sum().backward()
     assert torch.isfinite(loss).all() and ents[0].grad is not None
+
+
+def test_out_of_range_indices_are_flagged_not_followed():
+    """The reference raises IndexError (CPU) / a device-side assert (CUDA) on an index outside its table.  The kernels here
+    substitute row 0 and raise a flag in mapped host memory: nothing is read or written out of bounds (in particular the
+    gradient REDs of the scorers' backward), and the error surfaces as IndexError at the next index-consuming call or at
+    jmac_b200.check_errors()."""
+    import jmac_b200
+    from jmac_b200 import functional as JF
+    N, R, d, B, K = 500, 7, 64, 16, 4
+    torch.manual_seed(0)
+    ent = torch.randn(N, d, device="cuda", requires_grad=True)
+    rel = torch.randn(R, d, device="cuda", requires_grad=True)
+    guard = torch.zeros(4096, device="cuda")                        # allocated right behind the tables: must stay untouched
+    rng = np.random.default_rng(0)
+    h, r = np.tile(rng.integers(0, N, B), K + 1), np.tile(rng.integers(0, R, B), K + 1)
+    t = rng.integers(0, N, (K + 1) * B)
+    jmac_b200.check_errors()                                         # clean slate
+    loss = JF.transe_margin_loss([ent], [rel], h, r, t, B, 5.0)
+    loss.sum().backward()
+    jmac_b200.check_errors()                                         # valid indices: no flag
+    for bad_arr, name in ((t, "t"), (h, "h"), (r, "r")):
+        bad = bad_arr.copy()
+        bad[3] = 10 ** 6 if name != "r" else R                       # far outside / one past the end
+        args = {"h": h, "r": r, "t": t}
+        args[name] = bad
+        ent.grad = rel.grad = None
+        loss = JF.transe_margin_loss([ent], [rel], args["h"], args["r"], args["t"], B, 5.0)
+        loss.sum().backward()
+        with pytest.raises(IndexError):
+            jmac_b200.check_errors()
+        assert torch.isfinite(ent.grad).all() and float(guard.abs().max()) == 0.0
+        jmac_b200.check_errors()                                     # the flag was consumed
+    # negative index
+    bad = t.copy()
+    bad[0] = -1
+    JF.transe_margin_loss([ent.detach()], [rel.detach()], h, r, bad, B, 5.0)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):                                  # surfaces at the next index-consuming call without an explicit check
+        JF.transe_margin_loss([ent.detach()], [rel.detach()], h, r, t, B, 5.0)
+    # pair cosine and link prediction
+    A, Bm = torch.randn(50, d, device="cuda", requires_grad=True), torch.randn(60, d, device="cuda", requires_grad=True)
+    JF.pair_cos(A, Bm, [1, 2, 50], [3, 4, 5]).sum().backward()
+    with pytest.raises(IndexError):
+        jmac_b200.check_errors()
+    JF.l1_rank([ent.detach()], [rel.detach()], [1, 2], [0, R + 3], [5, 6])
+    with pytest.raises(IndexError):
+        jmac_b200.check_errors()
+    JF.l1_dist([ent.detach()], [rel.detach()], [1, N], [0, 1])
+    with pytest.raises(IndexError):
+        jmac_b200.check_errors()
+    with pytest.raises(ValueError):                                  # one index list addresses every layer's table: shapes must agree
+        JF.transe_margin_loss([ent.detach(), ent.detach()[:100]], [rel.detach(), rel.detach()], h, r, t, B, 5.0)
+    jmac_b200.check_errors()
+
+
+def test_forward_linkpred_index_list_and_gradient(golden):
+    """forward_linkpred with an all_index that is NOT range(N) selects / permutes the table first (src/jmac_model.py:304-306),
+    and the distances carry a gradient when one is requested."""
+    g = golden("model_noname")
+    n1, nr = int(g["n1"]), int(g["nr"])
+    model = model_pair(g, make_args(16))
+    model.eval()
+    ei1, et1 = T(g["ei1"]).cuda(), T(g["et1"]).cuda()
+    perm = np.random.default_rng(0).permutation(n1)
+    e, r = [0, 5, 7], [1, 2, 3]
+    with torch.no_grad():
+        full = model.forward_linkpred(e, r, ei1, et1, list(range(n1)), [0, n1], [0, nr])
+        sub = model.forward_linkpred(e, r, ei1, et1, perm.tolist(), [0, n1], [0, nr])
+        # reference semantics: table' = table[perm]; the query rows e index table'
+        ref = model.forward_linkpred(perm[e].tolist(), r, ei1, et1, list(range(n1)), [0, n1], [0, nr])[:, perm]
+    torch.testing.assert_close(sub, ref, rtol=1e-5, atol=1e-4)
+    assert not torch.equal(sub, full)
+    # a permutation that keeps the first and the last entry in place is still a permutation
+    p2 = np.arange(n1)
+    p2[[3, 4]] = p2[[4, 3]]
+    with torch.no_grad():
+        swapped = model.forward_linkpred(e, r, ei1, et1, p2.tolist(), [0, n1], [0, nr])
+    torch.testing.assert_close(swapped[:, 3], full[:, 4], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(swapped[:, 10], full[:, 10], rtol=1e-5, atol=1e-4)
+    # gradient path (differentiable library cdist): same values, and a gradient arrives at the embedding table
+    model.train()
+    dist = model.forward_linkpred(e, r, ei1, et1, list(range(n1)), [0, n1], [0, nr])
+    assert dist.requires_grad
+    dist.sum().backward()
+    assert model.ent_init_att_completion.grad is not None and float(model.ent_init_att_completion.grad.abs().sum()) > 0
+    # the frozen margin is re-read after a load_state_dict
+    m0 = model._margin()
+    sd2 = {k: v.clone() for k, v in model.state_dict().items()}
+    sd2["margin_completion"] = sd2["margin_completion"] + 2.0
+    model.load_state_dict(sd2)
+    assert abs(model._margin() - (m0 + 2.0)) < 1e-6

@@ -1,11 +1,13 @@
 """Accuracy of the 3xTF32 node GEMM variants against float64, and what it means for the LeakyReLU sign decisions
 of the attention logit z = P[i] + Q[j] - S[t] ("kinks").
 
-Run once per mode (the mode is read when the library is loaded):
-    for m in 0 1 3; do JMAC_GEMM_MODE=$m python tools/gemm_accuracy.py; done
-mode 0: lo = x - hi fed to the tensor core as is (its low 13 mantissa bits are dropped by the MMA), 3 products
+profiles/gemm_accuracy_r02.jsonl was recorded at commit a443bbe, where the kernel still had an experiment switch
+(JMAC_GEMM_MODE, removed afterwards because it changed nothing):
+mode 0: lo = x - hi fed to the tensor core as is (its low 13 mantissa bits are dropped by the MMA), 3 products  [what ships]
 mode 1: lo rounded to TF32 (RN) before the MMA, 3 products
 mode 3: lo rounded to TF32 + the lo.lo product (4 MMAs)
+All three: rms error 1.8e-7 of sum|a||b| (cuBLAS fp32: 2.8e-8), max 1.1-1.2e-6 -- the error is the tensor core's accumulation,
+not the operand split.
 Prints one JSON line: max / rms error of P = X W in units of sum|a||b| and of an fp32 FMA chain (cuBLAS fp32,
 TF32 disabled), and the number of sign decisions of z that differ from float64 on a 5000-node / 30001-edge graph."""
 import json
