@@ -154,6 +154,10 @@ int jmac_bn_tanh_bwd_apply(const float* gout, const float* out, const float* pre
  * ------------------------------------------------------------------------------------------ */
 int jmac_gemm_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
                      float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+/* The pre-split of the small operand in one pass: W[rows, cols] (leading dimension ld) -> hi = RN-to-TF32(w), lo = w - hi, both
+ * contiguous, laid out as W (transpose == 0) or as W^T [cols, rows] (transpose != 0: Y = X W needs B = W^T in [N,K] form). */
+int jmac_split_tf32(const float* W, int64_t rows, int64_t cols, int64_t ld, int transpose, float* hi,
+                    float* lo, void* stream);
 /* Same product with up to two [M,N] addends folded into the epilogue, C = A.B^T + D1 (+ D2); D1/D2
  * may alias C.  Fuses the gradient accumulation of the layer input (autograd's adds of
  * dP W_top^T, dQ W_bot^T, the edge pass's dX and the self-loop term, src/jmac_model.py:49-52,75-76). */

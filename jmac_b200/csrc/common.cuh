@@ -68,14 +68,22 @@ struct jmac_plan {
     // by relation
     int *typptr = nullptr, *typ_pos = nullptr, *typ_dst = nullptr;
     jmac::ItemList dst_items, src_items, typ_items;
-    // scratch for split segments (partials), grown lazily
+    // scratch for split segments (partials), grown lazily (stream-ordered allocation on the stream of the call that grows it)
     float* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // last use of the plan's arrays per stream (up to 4 streams): jmac_plan_destroy orders the frees behind these events instead
+    // of synchronising the device
+    cudaEvent_t use_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t use_st[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_use = 0;
+    bool many_streams = false;
 };
 
 namespace jmac {
 
-int plan_scratch(jmac_plan* p, size_t bytes, float** out);
+int plan_scratch(jmac_plan* p, size_t bytes, float** out, cudaStream_t st);
+// to be called after the last launch of an entry point that read the plan's arrays on `st`
+void plan_mark_use(jmac_plan* p, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

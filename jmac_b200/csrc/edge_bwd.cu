@@ -163,23 +163,37 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
 }
 
 // Sum of the partial rows of split segments: out[seg] = sum_k partial[first + k]; `rows` rows per slot.
+// One CTA of 8 warps per split: warp w adds the slots w, w + 8, ..., the eight warp sums are combined in a fixed order.
 template <int VPL>
 __global__ void __launch_bounds__(256) sum_partials_kernel(const Split* __restrict__ splits, int n_splits, const float* __restrict__ partial,
                                                            int d4, int rows, float* __restrict__ out0, float* __restrict__ out1) {
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_splits) return;
-    const Split sp = splits[w];
+    __shared__ float4 s_acc[8][VPL * 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= n_splits) return;
+    const Split sp = splits[blockIdx.x];
     for (int r = 0; r < rows; ++r) {
         Row<VPL> acc;
         acc.zero();
-        for (int k = 0; k < sp.count; ++k) {
+        for (int k = wib; k < sp.count; k += 8) {
             Row<VPL> part;
             load_row<VPL, true>(part, partial, (int64_t)(sp.first + k) * rows + r, d4, lane);
 #pragma unroll
             for (int i = 0; i < VPL; ++i) acc.v[i] = acc.v[i] + part.v[i];
         }
-        store_row<VPL>(acc, r == 0 ? out0 : out1, sp.seg, d4, lane);
+        __syncthreads();                                   // previous round's readers are done with s_acc
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) s_acc[wib][i * 32 + lane] = acc.v[i];
+        __syncthreads();
+        if (wib == 0) {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                float4 t = s_acc[0][i * 32 + lane];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) t = t + s_acc[w][i * 32 + lane];
+                acc.v[i] = t;
+            }
+            store_row<VPL>(acc, r == 0 ? out0 : out1, sp.seg, d4, lane);
+        }
     }
 }
 
@@ -667,7 +681,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
     p.da = da_att;
     p.partial = nullptr;
     if (plan->dst_items.n_slots > 0) {
-        int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)d, &p.partial);
+        int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)d, &p.partial, st);
         if (rc) return rc;
     }
     if (p.n_items == 0) return 0;
@@ -686,11 +700,11 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
         }
         JMAC_LAUNCH_CHECK();
         if (plan->dst_items.n_splits > 0) {
-            int mb = (plan->dst_items.n_splits * 32 + threads - 1) / threads;
-            sum_partials_kernel<VPL><<<mb, threads, 0, st>>>(plan->dst_items.splits, plan->dst_items.n_splits, p.partial, p.d4, 1, dP, nullptr);
+            sum_partials_kernel<VPL><<<plan->dst_items.n_splits, threads, 0, st>>>(plan->dst_items.splits, plan->dst_items.n_splits, p.partial, p.d4, 1, dP, nullptr);
             JMAC_LAUNCH_CHECK();
         }
     });
+    plan_mark_use(plan, st);
     return 0;
 }
 
@@ -715,7 +729,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
         JMAC_CUDA(cudaMemsetAsync(out_w, 0, sizeof(float) * (size_t)plan->n_rel * d, st));
         JMAC_CUDA(cudaMemsetAsync(out_z, 0, sizeof(float) * (size_t)plan->n_rel * d, st));
     } else if (il.n_slots > 0) {
-        int rc = plan_scratch(plan, sizeof(float) * (size_t)il.n_slots * 2 * (size_t)d, &p.partial);
+        int rc = plan_scratch(plan, sizeof(float) * (size_t)il.n_slots * 2 * (size_t)d, &p.partial, st);
         if (rc) return rc;
     }
     if (p.n_items == 0) return 0;
@@ -737,8 +751,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
             }
             JMAC_LAUNCH_CHECK();
             if (il.n_splits > 0) {
-                int mb = (il.n_splits * 32 + threads - 1) / threads;
-                sum_partials_kernel<VPL><<<mb, threads, 0, st>>>(il.splits, il.n_splits, p.partial, p.d4, 2, out_w, out_z);
+                sum_partials_kernel<VPL><<<il.n_splits, threads, 0, st>>>(il.splits, il.n_splits, p.partial, p.d4, 2, out_w, out_z);
                 JMAC_LAUNCH_CHECK();
             }
         } else {
@@ -754,6 +767,7 @@ static int gather_pass(jmac_plan* plan, int mode, const float* G, const void* er
             JMAC_LAUNCH_CHECK();
         }
     });
+    plan_mark_use(plan, st);
     return 0;
 }
 

@@ -409,24 +409,32 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
     if (save && batch_base + lane < stream_end) p.logit[batch_base + lane] = sc_keep;
 }
 
-// Two-level softmax merge for split (hub) destinations: one warp per split segment.
+// Two-level softmax merge for split (hub) destinations: one CTA of 8 warps per split segment.  Warp w combines the slots
+// w, w + 8, ... (a hub of the reference's graphs has up to ~90 slots of 32 edges; walking them with one warp serialised ~90
+// dependent row loads), the eight warp results are then added in a fixed order (deterministic).
 template <int VPL>
 __global__ void __launch_bounds__(256) edge_fwd_merge_kernel(EdgeFwdParams fp, const Split* __restrict__ splits, int n_splits,
                                                              const float* __restrict__ partial, const float* __restrict__ sqrt_deg,
                                                              int d4, float* __restrict__ agg, float* __restrict__ lse) {
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_splits) return;
-    const Split sp = splits[w];
+    __shared__ float s_max[8], s_l[8];
+    __shared__ float4 s_acc[8][VPL * 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= n_splits) return;
+    const Split sp = splits[blockIdx.x];
     const size_t stride = (size_t)(d4 * 4 + 4);
     const float* base = partial + (size_t)sp.first * stride;
     float M = -INFINITY;
-    for (int k = lane; k < sp.count; k += 32) M = fmaxf(M, base[k * stride]);
+    for (int k = threadIdx.x; k < sp.count; k += 256) M = fmaxf(M, base[k * stride]);
     M = warp_max(M);
+    if (lane == 0) s_max[wib] = M;
+    __syncthreads();
+    M = s_max[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) M = fmaxf(M, s_max[w]);
     float L = 0.f;
     Row<VPL> acc;
     acc.zero();
-    for (int k = 0; k < sp.count; ++k) {
+    for (int k = wib; k < sp.count; k += 8) {
         const float4 ml = *reinterpret_cast<const float4*>(base + k * stride);
         const float sc = ml.y > 0.f ? __expf(ml.x - M) : 0.f;
         L += sc * ml.y;
@@ -435,12 +443,28 @@ __global__ void __launch_bounds__(256) edge_fwd_merge_kernel(EdgeFwdParams fp, c
 #pragma unroll
         for (int i = 0; i < VPL; ++i) fma4(acc.v[i], sc, part.v[i]);
     }
-    const float inv = L > 0.f ? sqrt_deg[sp.seg] / L : 0.f;
+    if (lane == 0) s_l[wib] = L;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
-    store_row<VPL>(acc, agg, sp.seg, d4, lane);
-    if (fp.T) store_self_fused<VPL>(fp, acc, sp.seg, d4, lane);
-    if (lane == 0) lse[sp.seg] = L > 0.f ? M + logf(L) : 0.f;
+    for (int i = 0; i < VPL; ++i) s_acc[wib][i * 32 + lane] = acc.v[i];
+    __syncthreads();
+    if (wib == 0) {
+        L = s_l[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) L += s_l[w];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            float4 t = s_acc[0][i * 32 + lane];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) t = t + s_acc[w][i * 32 + lane];
+            acc.v[i] = t;
+        }
+        const float inv = L > 0.f ? sqrt_deg[sp.seg] / L : 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) acc.v[i] = inv * acc.v[i];
+        store_row<VPL>(acc, agg, sp.seg, d4, lane);
+        if (fp.T) store_self_fused<VPL>(fp, acc, sp.seg, d4, lane);
+        if (lane == 0) lse[sp.seg] = L > 0.f ? M + logf(L) : 0.f;
+    }
 }
 
 }  // namespace jmac
@@ -477,7 +501,7 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
     p.loop_row = Rp + (size_t)(plan->n_rel - 1) * d;     // the self-loop relation is the last row of R'
     p.partial = nullptr;
     if (plan->dst_items.n_slots > 0) {
-        int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)(d + 4), &p.partial);
+        int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)(d + 4), &p.partial, st);
         if (rc) return rc;
     }
     if (p.n_items == 0) return 0;
@@ -503,11 +527,11 @@ extern "C" int jmac_edge_fwd_fused(jmac_plan* plan, const float* P, const float*
         }
         JMAC_LAUNCH_CHECK();
         if (plan->dst_items.n_splits > 0) {
-            int mb = (plan->dst_items.n_splits * 32 + threads - 1) / threads;
-            edge_fwd_merge_kernel<VPL><<<mb, threads, 0, st>>>(p, plan->dst_items.splits, plan->dst_items.n_splits, p.partial,
+            edge_fwd_merge_kernel<VPL><<<plan->dst_items.n_splits, threads, 0, st>>>(p, plan->dst_items.splits, plan->dst_items.n_splits, p.partial,
                                                                 plan->sqrt_deg, p.d4, agg, lse);
             JMAC_LAUNCH_CHECK();
         }
     });
+    plan_mark_use(plan, st);
     return 0;
 }

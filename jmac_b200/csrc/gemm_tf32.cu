@@ -466,6 +466,21 @@ __global__ void __launch_bounds__(256) sum_partials_f32_kernel(const float* __re
     }
 }
 
+// The small (weight) operand of a node product, pre-split for the 3xTF32 kernel in one pass: hi = RN-to-TF32(w), lo = w - hi, written
+// as [rows, cols] (transpose == 0) or as the transposed [cols, rows] table (transpose != 0), both contiguous.
+__global__ void split_tf32_kernel(const float* __restrict__ W, int rows, int cols, int64_t ld, int transpose, float* __restrict__ hi,
+                                  float* __restrict__ lo) {
+    const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (o >= (int64_t)rows * cols) return;
+    int64_t src;
+    if (!transpose) src = (o / cols) * ld + (o % cols);
+    else src = (o % rows) * ld + (o / rows);
+    const float x = W[src];
+    const float h = tf32_rna(x);
+    hi[o] = h;
+    lo[o] = x - h;
+}
+
 int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int feat, int64_t ld) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return JMAC_EINVAL; }
@@ -484,6 +499,14 @@ int make_map_f32_mn(CUtensorMap* map, const void* ptr, int64_t rows, int feat, i
 
 using namespace jmac;
 
+extern "C" int jmac_split_tf32(const float* W, int64_t rows, int64_t cols, int64_t ld, int transpose, float* hi, float* lo, void* stream) {
+    JMAC_ARG(W && hi && lo && rows > 0 && cols > 0 && ld >= cols && rows * cols < (int64_t(1) << 31));
+    const int64_t n = rows * cols;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, (int)rows, (int)cols, ld, transpose, hi, lo);
+    JMAC_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" size_t jmac_gemm_tn_workspace_bytes(int KO, int N) { return (size_t)sm_count() * (size_t)KO * (size_t)N * sizeof(float); }
 
 extern "C" int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, int64_t ldg, float* D, int64_t M, int KO, int N,
@@ -497,8 +520,12 @@ extern "C" int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, 
     if (rc) return rc;
     rc = make_map_f32_mn(&map_g, G, M, N, ldg);
     if (rc) return rc;
+    // every CTA writes a [KO, N] partial (256 KB at 256 x 256) that the second kernel reads back: at least 256 rows per CTA, so that
+    // on the reference's graph sizes (5-14 k nodes) the partial traffic does not dwarf the operands
     const int64_t blocks_of_rows = (M + T_BR - 1) / T_BR;
     int grid = sm_count();
+    const int64_t by_rows = (M + 255) / 256;
+    if (by_rows < grid) grid = (int)by_rows;
     if (blocks_of_rows < grid) grid = (int)blocks_of_rows;
     GemmTnParams p;
     p.M = (int)M; p.KO = KO; p.N = N;

@@ -51,16 +51,19 @@ int sm_count() {
 // cost milliseconds per 100 MB block, which made rebuilding a 40M-edge plan (a triple-transfer round, train.py:471-472,
 // or the host-fed bench step) slower than the sorts themselves.  The default memory pool keeps freed blocks
 // (release threshold = max), so a rebuilt plan reuses the memory of the destroyed one without touching the OS.
+// Bounded: at most 8 GiB of freed plan memory stay cached per device (a C4 plan with its sort temporaries is ~4 GB); beyond that
+// the pool hands memory back at the next synchronisation, so PyTorch's allocator is not starved.  Set once per device.
 static void pool_setup() {
-    static bool done = false;
-    if (done) return;
+    static unsigned long long done_mask = 0;       // bit per device ordinal (< 64)
     int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    const unsigned long long bit = 1ULL << dev;
+    if (__atomic_fetch_or(&done_mask, bit, __ATOMIC_RELAXED) & bit) return;
     cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = 8ULL << 30;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    done = true;
 }
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t bytes, cudaStream_t st) {
@@ -89,16 +92,40 @@ struct Temps {
     }
 };
 
-int plan_scratch(jmac_plan* p, size_t bytes, float** out) {
+int plan_scratch(jmac_plan* p, size_t bytes, float** out, cudaStream_t st) {
     if (bytes > p->scratch_bytes) {
-        if (p->scratch) JMAC_CUDA(cudaFree(p->scratch));
+        // stream-ordered: earlier kernels of this stream that still read the old block finish before it is recycled
+        if (p->scratch) dfree(p->scratch, st);
         p->scratch = nullptr;
         p->scratch_bytes = 0;
-        JMAC_CUDA(cudaMalloc(&p->scratch, bytes));
+        JMAC_CUDA(dmalloc(&p->scratch, bytes, st));
         p->scratch_bytes = bytes;
     }
     *out = p->scratch;
     return 0;
+}
+
+void plan_mark_use(jmac_plan* p, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cs != cudaStreamCaptureStatusNone) return;      // captured launches: the owner of the graph keeps the plan alive (jmac_b200.graphs)
+    int i = 0;
+    while (i < p->n_use && p->use_st[i] != st) ++i;
+    if (i == p->n_use) {
+        if (p->n_use == 4) { p->many_streams = true; return; }
+        if (cudaEventCreateWithFlags(&p->use_ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); p->many_streams = true; return; }
+        p->use_st[i] = st;
+        ++p->n_use;
+    }
+    cudaEventRecord(p->use_ev[i], st);
+}
+
+// one non-blocking stream per device on which destroyed plans are freed, behind their last-use events
+static cudaStream_t free_stream(int dev) {
+    static cudaStream_t fs[64] = {};
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!fs[dev] && cudaStreamCreateWithFlags(&fs[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); fs[dev] = nullptr; }
+    return fs[dev];
 }
 
 static int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
@@ -264,17 +291,22 @@ extern "C" int jmac_status_poll(void) {
 
 extern "C" int jmac_plan_destroy(jmac_plan* p) {
     if (!p) return 0;
-    // One device-wide wait (any stream may still be reading the plan), then stream-ordered frees back into the pool:
-    // the ~20 cudaFree calls this replaces each synchronised the device and returned the memory to the OS.
+    // No host-side wait: the frees are stream-ordered on a per-device "free" stream that first waits for the last kernel that read
+    // the plan on every stream it was used on (plan_mark_use).  The memory goes back to the pool (not to the OS), so a rebuilt plan
+    // reuses it.  Only a plan used from more than four streams falls back to one device-wide wait.
     int cur = p->device;
     cudaGetDevice(&cur);
     if (cur != p->device) cudaSetDevice(p->device);      // a process that drives several devices may destroy the plan from another one
-    cudaDeviceSynchronize();
+    cudaStream_t fs = free_stream(p->device);
+    if (p->many_streams || fs == nullptr) cudaDeviceSynchronize();
+    for (int i = 0; i < p->n_use; ++i) {
+        if (fs) cudaStreamWaitEvent(fs, p->use_ev[i], 0);
+    }
     void* ptrs[] = {p->rowptr, p->csr_src, p->csr_type, p->csr_eid, p->csr_dst, p->sqrt_deg, p->colptr, p->csc_pos, p->csc_dst, p->typptr,
                     p->typ_pos, p->typ_dst, p->dst_items.items, p->dst_items.splits, p->src_items.items, p->src_items.splits,
-                    p->typ_items.items, p->typ_items.splits};
-    for (void* q : ptrs) dfree(q, 0);
-    if (p->scratch) cudaFree(p->scratch);
+                    p->typ_items.items, p->typ_items.splits, p->scratch};
+    for (void* q : ptrs) dfree(q, fs);
+    for (int i = 0; i < p->n_use; ++i) cudaEventDestroy(p->use_ev[i]);      // released once the recorded work has completed
     if (cur != p->device) cudaSetDevice(cur);
     delete p;
     return 0;
@@ -414,5 +446,6 @@ extern "C" int jmac_plan_export(const jmac_plan* p, int32_t* rowptr, int32_t* cs
     if (csr_type && p->E) JMAC_CUDA(cudaMemcpyAsync(csr_type, p->csr_type, sizeof(int) * (size_t)p->E, cudaMemcpyDeviceToDevice, st));
     if (csr_eid && p->E) JMAC_CUDA(cudaMemcpyAsync(csr_eid, p->csr_eid, sizeof(int) * (size_t)p->E, cudaMemcpyDeviceToDevice, st));
     if (sqrt_deg) JMAC_CUDA(cudaMemcpyAsync(sqrt_deg, p->sqrt_deg, sizeof(float) * (size_t)p->N, cudaMemcpyDeviceToDevice, st));
+    plan_mark_use(const_cast<jmac_plan*>(p), st);
     return 0;
 }

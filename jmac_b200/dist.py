@@ -249,15 +249,15 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
             Xf, works = x_full.detach().index_select(0, shard.gather_map(dev)), [None] * shard.chunks
         else:
             Xf, works = gather_rows(x_loc.detach(), shard, group, async_op=True)
-        P = JF.gemm_nt(x_loc, Wt.t().contiguous())                 # runs under the first chunk of the all-gather
-        S = Rp @ Wb
-        WbT = Wb.t().contiguous()
+        P = JF.gemm_nn(x_loc, Wt)                                  # runs under the first chunk of the all-gather
+        S = JF.small_mm(Rp, Wb)
+        wb_hi, wb_lo = JF._split_weight(Wb, True)                   # split once, used by every chunk
         Q = torch.empty_like(Xf)
         for c in range(shard.chunks):
             if works[c] is not None:
                 works[c].wait()                                     # the compute stream waits for chunk c only
             r0, r1 = shard.chunk_rows(c)
-            JF.gemm_nt(Xf[r0:r1], WbT, out=Q[r0:r1])
+            JF._gemm_presplit(Xf[r0:r1], wb_hi, wb_lo, out=Q[r0:r1])
         agg, T = torch.empty_like(x_loc), torch.empty_like(x_loc)
         lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad)
@@ -291,26 +291,27 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
             check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
                   "jmac_edge_bwd_src")
         # the partial input gradient of every gathered row, chunk by chunk, each chunk handed to NCCL as soon as it exists
-        Wbc = Wb.contiguous()
+        wb_hi, wb_lo = JF._split_weight(Wb, False)
         scattered = torch.empty(shard.n_max, d, dtype=torch.float32, device=dev)
         works = []
         for c in range(shard.chunks):
             r0, r1 = shard.chunk_rows(c)
-            JF.gemm_nt(dQ[r0:r1], Wbc, add1=dXe[r0:r1], out=dXe[r0:r1])          # dQ W_bot^T + dXe, in place
+            JF._gemm_presplit(dQ[r0:r1], wb_hi, wb_lo, add1=dXe[r0:r1], out=dXe[r0:r1])      # dQ W_bot^T + dXe, in place
             works.append(scatter_sum_chunk(dXe[r0:r1], scattered[c * shard.n_c:(c + 1) * shard.n_c], shard, group, async_op=True))
         # ... under which the rest of the node's backward runs on the compute stream
         with torch.cuda.device(dev):
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), stream_ptr()),
                   "jmac_edge_bwd_rel")
         dRp[-1] -= G.sum(0)                                   # T = agg + x_loc - Rp[-1]
-        dRp += dS @ Wb.t()                                    # S = Rp Wb
-        dXd = JF.gemm_nt(dP, Wt.contiguous(), add1=G)         # dP W_top^T + dT
+        JF.small_mm_nt_acc(dS, Wb, dRp)                       # S = Rp Wb: dRp += dS Wb^T
+        dXd = JF.gemm_nt(dP, Wt, add1=G)                      # dP W_top^T + dT
         dW = None
         if ctx.needs_input_grad[3]:
-            dWt = JF.gemm_tn(x_loc, dP)
+            dW = torch.empty_like(W_att)
+            dW[:d] = JF.gemm_tn(x_loc, dP)
             dWb = JF.gemm_tn(Xf, dQ)
-            dWb += Rp.t() @ dS
-            dW = torch.cat([dWt, dWb], dim=0)
+            dWb += JF.small_mm_tn(Rp, dS)
+            dW[d:] = dWb
         for w in works:
             if w is not None:
                 w.wait()

@@ -104,8 +104,7 @@ _PLAN_PINS: Optional[list] = None      # while a CUDA graph is being captured (j
 def get_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int) -> GraphPlan:
     """Plan cache keyed on tensor identity + version: the reference reuses one edge set for
     thousands of optimiser steps (train.py:447-485) and rebuilds tensors when the graph changes."""
-    key = (edge_index.data_ptr(), edge_type.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_type._version,
-           int(num_ent), int(n_rel), str(edge_index.device))
+    key = _plan_key(edge_index, edge_type, num_ent, n_rel)
     hit = _PLAN_CACHE.get(key)
     if hit is not None:
         _PLAN_CACHE.move_to_end(key)
@@ -120,6 +119,19 @@ def get_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_
     if _PLAN_PINS is not None:
         _PLAN_PINS.append(plan)
     return plan
+
+
+def _plan_key(edge_index, edge_type, num_ent, n_rel):
+    return (edge_index.data_ptr(), edge_type.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_type._version,
+            int(num_ent), int(n_rel), str(edge_index.device))
+
+
+def register_plan(edge_index: torch.Tensor, edge_type: torch.Tensor, num_ent: int, n_rel: int, plan: GraphPlan):
+    """Put a plan that was built ahead of time (e.g. on a copy stream while the previous step computes) into the cache under
+    the key the layers will look it up with."""
+    _PLAN_CACHE[_plan_key(edge_index, edge_type, num_ent, n_rel)] = (plan, edge_index, edge_type)
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
 
 
 def get_edge_table_plan(edge_index: torch.Tensor, num_ent: int) -> GraphPlan:
@@ -234,9 +246,9 @@ class AttnEdgeFn(torch.autograd.Function):
         if N != plan.N or Xs.shape[0] != plan.N_src or Rp.shape[0] != plan.n_rel:
             raise ValueError("table sizes do not match the graph plan")
         Wt, Wb = W_att[:d], W_att[d:]
-        P = gemm_nt(Xd, Wt.t().contiguous())
-        Q = gemm_nt(Xs, Wb.t().contiguous())
-        S = Rp @ Wb
+        P = gemm_nn(Xd, Wt)
+        Q = gemm_nn(Xs, Wb)
+        S = small_mm(Rp, Wb)
         agg = torch.empty_like(Xd)
         T = torch.empty_like(Xd)
         lse = torch.empty(N, dtype=torch.float32, device=Xd.device)
@@ -271,22 +283,23 @@ class AttnEdgeFn(torch.autograd.Function):
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st),
                   "jmac_edge_bwd_rel")
         dRp[-1] -= G.sum(0)                                   # T = agg + Xd - Rp[-1]
-        dRp += dS @ Wb.t()                                    # S = Rp Wb
+        small_mm_nt_acc(dS, Wb, dRp)                          # S = Rp Wb: dRp += dS Wb^T
         dXd = dXs = dW = None
         if same:
             if ctx.needs_input_grad[1]:
-                dXd = gemm_nt(dP, Wt.contiguous(), add1=dXe, add2=G, out=dXe)    # dP Wt^T + dXe + dT, in place over dXe
-                dXd = gemm_nt(dQ, Wb.contiguous(), add1=dXd, out=dXd)             # + dQ Wb^T
+                dXd = gemm_nt(dP, Wt, add1=dXe, add2=G, out=dXe)                  # dP Wt^T + dXe + dT, in place over dXe
+                dXd = gemm_nt(dQ, Wb, add1=dXd, out=dXd)                          # + dQ Wb^T
         else:
             if ctx.needs_input_grad[1]:
-                dXd = gemm_nt(dP, Wt.contiguous(), add1=G)                        # dP Wt^T + dT
+                dXd = gemm_nt(dP, Wt, add1=G)                                     # dP Wt^T + dT
             if ctx.needs_input_grad[2]:
-                dXs = gemm_nt(dQ, Wb.contiguous(), add1=dXe, out=dXe)             # dQ Wb^T + dXe: the partial that is reduce-scattered
+                dXs = gemm_nt(dQ, Wb, add1=dXe, out=dXe)                          # dQ Wb^T + dXe: the partial that is reduce-scattered
         if ctx.needs_input_grad[3]:
-            dWt = gemm_tn(Xd, dP)
+            dW = torch.empty_like(W_att)
+            dW[:d] = gemm_tn(Xd, dP)
             dWb = gemm_tn(Xs, dQ)
-            dWb += Rp.t() @ dS
-            dW = torch.cat([dWt, dWb], dim=0)
+            dWb += small_mm_tn(Rp, dS)
+            dW[d:] = dWb
         return None, dXd, dXs, dW, dRp, da.view(ctx.a_shape), None
 
 
@@ -302,22 +315,28 @@ def attn_edge(plan, X, W_att, Rp, a_att, slope, X_src=None):
 # ----------------------------------------------------------------------------------------------
 # node-level dense products (3xTF32 on tcgen05, fp32-accurate)
 # ----------------------------------------------------------------------------------------------
-def _split_tf32(w_nk: torch.Tensor):
-    """hi = w rounded to nearest TF32 (ties away, like cvt.rna.tf32.f32; low 13 mantissa bits zero),
-    lo = w - hi (exact in fp32)."""
-    hi = ((w_nk.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
-    return hi, w_nk - hi
-
-
-def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
-    """C[M,N] = A[M,K] @ B_nk[N,K]^T (+ add1 + add2) through jmac_gemm_tf32x3_add (raises on unsupported shapes).
-    ``add1``/``add2``: [M,N] contiguous addends folded into the epilogue; ``out`` may be one of them (in-place accumulate)."""
+def _split_weight(W: torch.Tensor, transpose: bool):
+    """The small operand of a node product, pre-split for the 3xTF32 kernel by ONE launch: hi = W rounded to nearest TF32
+    (ties away, cvt.rna.tf32.f32), lo = W - hi (exact in fp32), laid out as W or as W^T (contiguous)."""
     lib = _lib.load()
-    _need_cuda(A, B_nk)
-    A, B_nk = _f32c(A), _f32c(B_nk)
+    if W.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {W.dtype}")
+    if W.stride(1) != 1:
+        W = W.contiguous()
+    rows, cols = W.shape
+    shape = (cols, rows) if transpose else (rows, cols)
+    hi = torch.empty(shape, dtype=torch.float32, device=W.device)
+    lo = torch.empty(shape, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        check(lib.jmac_split_tf32(ptr(W), rows, cols, W.stride(0), int(bool(transpose)), ptr(hi), ptr(lo), stream_ptr()), "jmac_split_tf32")
+    return hi, lo
+
+
+def _gemm_presplit(A: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
+    lib = _lib.load()
+    A = _f32c(A)
     M, K = A.shape
-    N = B_nk.shape[0]
-    hi, lo = _split_tf32(B_nk)
+    N = hi.shape[0]
     C = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=A.device)
     for t in (add1, add2, out):
         if t is not None and (t.shape != (M, N) or t.dtype != torch.float32 or not t.is_contiguous()):
@@ -328,6 +347,25 @@ def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor, add1=None, add2=None, out=None)
         check(lib.jmac_gemm_tf32x3_add(ptr(A), K, ptr(hi), ptr(lo), K, ptr(C), N, M, N, K, ptr(add1), ptr(add2), N, stream_ptr()),
               "jmac_gemm_tf32x3_add")
     return C
+
+
+def gemm_nt(A: torch.Tensor, B_nk: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ B_nk[N,K]^T (+ add1 + add2) through jmac_gemm_tf32x3_add (raises on unsupported shapes).
+    ``add1``/``add2``: [M,N] contiguous addends folded into the epilogue; ``out`` may be one of them (in-place accumulate)."""
+    _need_cuda(A, B_nk)
+    if B_nk.shape[1] != A.shape[1]:
+        raise ValueError("inner dimensions differ")
+    hi, lo = _split_weight(B_nk, False)
+    return _gemm_presplit(A, hi, lo, add1, add2, out)
+
+
+def gemm_nn(A: torch.Tensor, W_kn: torch.Tensor, add1=None, add2=None, out=None) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ W_kn[K,N] (+ addends): the transposition of the weight is folded into its split pass."""
+    _need_cuda(A, W_kn)
+    if W_kn.shape[0] != A.shape[1]:
+        raise ValueError("inner dimensions differ")
+    hi, lo = _split_weight(W_kn, True)
+    return _gemm_presplit(A, hi, lo, add1, add2, out)
 
 
 def gemm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
@@ -345,12 +383,38 @@ def gemm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     return D
 
 
+_TC_MIN_ROWS = 512      # below this a 256-row tile grid cannot hide its pipeline fill: the library product is as fast
+
+
+def small_mm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """A @ W for the relation tables (a few hundred to a few thousand rows): the tensor-core kernel when its tile grid pays,
+    the library product otherwise.  No autograd (used inside the autograd nodes)."""
+    if _tc_eligible(A.shape[0], A.shape[1], W.shape[1]):
+        return gemm_nn(A, W)
+    return A @ W
+
+
+def small_mm_nt_acc(A: torch.Tensor, W: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
+    """acc += A @ W^T, in place."""
+    if _tc_eligible(A.shape[0], A.shape[1], W.shape[0]) and acc.is_contiguous():
+        return gemm_nt(A, W, add1=acc, out=acc)
+    acc += A @ W.t()
+    return acc
+
+
+def small_mm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
+    """X^T @ G."""
+    if _tn_eligible(X.shape[0], X.shape[1], G.shape[1]):
+        return gemm_tn(X, G)
+    return X.t() @ G
+
+
 def _tn_eligible(M, KO, N) -> bool:
-    return M >= 4096 and KO in (128, 256) and N % 32 == 0 and 32 <= N <= 256
+    return M >= _TC_MIN_ROWS and KO in (128, 256) and N % 32 == 0 and 32 <= N <= 256
 
 
 def _tc_eligible(M, K, N) -> bool:
-    return M >= 4096 and N % 32 == 0 and 32 <= N <= 256 and K % 16 == 0 and K >= 16
+    return M >= _TC_MIN_ROWS and N % 32 == 0 and 32 <= N <= 256 and K % 16 == 0 and K >= 16
 
 
 class NodeMatmulFn(torch.autograd.Function):
@@ -359,7 +423,7 @@ class NodeMatmulFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, W):
         ctx.save_for_backward(X, W)
-        return gemm_nt(X, W.t().contiguous())
+        return gemm_nn(X, W)
 
     @staticmethod
     def backward(ctx, G):
@@ -368,7 +432,7 @@ class NodeMatmulFn(torch.autograd.Function):
         dX = dW = None
         if ctx.needs_input_grad[0]:
             M, N = G.shape
-            dX = gemm_nt(G, W.contiguous()) if _tc_eligible(M, N, W.shape[0]) else G @ W.t()
+            dX = gemm_nt(G, W) if _tc_eligible(M, N, W.shape[0]) else G @ W.t()
         if ctx.needs_input_grad[1]:
             dW = gemm_tn(X, G) if _tn_eligible(X.shape[0], X.shape[1], G.shape[1]) else X.t() @ G
         return dX, dW

@@ -62,9 +62,9 @@ class RelationAwareLayer(nn.Module):
 
     def relation_transform(self, rel_emb):
         rel = torch.cat([rel_emb, self.loop_rel], dim=0)                        # :39
-        rel = torch.mm(rel, self.rel_transform_weight1)                         # :40
+        rel = JF.node_mm(rel, self.rel_transform_weight1)                       # :40  (tensor-core product from 512 rows up, library below)
         rel = F.leaky_relu(rel, self.leaky_slope) if self.rel_act == "leaky" else F.relu(rel)   # :41
-        return torch.mm(rel, self.rel_transform_weight2)                        # :42
+        return JF.node_mm(rel, self.rel_transform_weight2)                      # :42
 
     def forward(self, ent_emb, rel_emb, edge_index, edge_type):
         if self.comp_op == "mult":
@@ -219,7 +219,7 @@ class JMAC(BaseModel):
         comp_embs, comp_rels = [e0], [r0]
         if self.args.num_gcn_layer == 2:
             e1 = self.conv1_completion(e0, r0, edge_index, edge_type)
-            r1 = torch.mm(self.atv_mlp(torch.mm(r0, self.rel_linear11)), self.rel_linear12)
+            r1 = JF.node_mm(self.atv_mlp(JF.node_mm(r0, self.rel_linear11)), self.rel_linear12)
             comp_embs.append(e1)
             comp_rels.append(r1)
         return comp_embs[-1], comp_embs, comp_rels

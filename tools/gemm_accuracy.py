@@ -30,7 +30,7 @@ def main():
     torch.nn.init.xavier_normal_(W)
     ref = X.double() @ W.double()
     bound = X.abs().double() @ W.abs().double()
-    ours = JF.gemm_nt(X, W.t().contiguous()).double()
+    ours = JF.gemm_nn(X, W).double()
     lib = (X @ W).double()
     out = {"mode": int(os.environ.get("JMAC_GEMM_MODE", "0")),
            "max_err_over_bound": float(((ours - ref).abs() / bound).max()), "rms_err_over_bound": float((((ours - ref) / bound) ** 2).mean().sqrt()),
@@ -49,8 +49,8 @@ def main():
     z64 = torch.cat([Xn[i], Xn[j] - Rp[t]], 1).double() @ Wa.double()
     z_ref32 = torch.cat([Xn[i], Xn[j] - Rp[t]], 1) @ Wa                                   # the reference's fp32 formulation
     Wt, Wb = Wa[:K], Wa[K:]
-    P = JF.gemm_nt(Xn.repeat(2, 1)[:8192], Wt.t().contiguous())[:n]                        # the tensor-core path needs >= 4096 rows
-    Q = JF.gemm_nt(Xn.repeat(2, 1)[:8192], Wb.t().contiguous())[:n]
+    P = JF.gemm_nn(Xn, Wt)
+    Q = JF.gemm_nn(Xn, Wb)
     S = Rp @ Wb
     z_ours = P[i] + Q[j] - S[t]
     out["sign_flips_vs_f64"] = {"ours": int(((z_ours > 0) != (z64 > 0)).sum()), "reference_fp32": int(((z_ref32 > 0) != (z64 > 0)).sum()),
