@@ -47,12 +47,14 @@ int jmac_status_poll(void);
  * once per edge set; the reference reuses one edge set for thousands of steps (train.py:447-485).
  *   row = edge_index[0] (aggregation target i), col = edge_index[1] (message source j).
  *   n_rel = number of relation rows INCLUDING the self-loop row (= rel_emb.size(0) + 1).
- *   chunk = max edges one warp handles before a segment is split (0 = default 256).
+ *   chunk = max edges one warp handles before a segment is split; 0 = automatic: 256 on large graphs, down to 32 on the
+ *           reference's graph sizes, where a warp's fair share of the edges is a few dozen.
  * Synchronises `stream` (it needs data-dependent sizes); the plan is complete on return and may be
  * used from any stream.  Its arrays come from the device's default stream-ordered memory pool
- * (cudaMallocAsync; the pool keeps freed blocks, so a rebuilt plan reuses the memory of the
- * destroyed one).  jmac_plan_destroy waits for the device (any stream may still be reading the
- * plan) and returns the arrays to that pool.  A plan owns the scratch for the partial results of
+ * (cudaMallocAsync; the pool keeps up to 8 GiB of freed blocks per device, so a rebuilt plan reuses the
+ * memory of the destroyed one).  jmac_plan_destroy does not synchronise the device: every entry point
+ * records an event behind its last kernel, the frees are ordered behind those events on a private stream
+ * and the call waits for that stream only.  A plan owns the scratch for the partial results of
  * split segments: edge kernels of ONE plan must not run concurrently on different streams.
  * ------------------------------------------------------------------------------------------ */
 typedef struct jmac_plan jmac_plan;

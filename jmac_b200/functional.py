@@ -383,7 +383,10 @@ def gemm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     return D
 
 
-_TC_MIN_ROWS = 512      # below this a 256-row tile grid cannot hide its pipeline fill: the library product is as fast
+# Measured on the DBP-5L-shaped step (profiles/c2_step_launches_r02.md): for the 962-row relation tables the tcgen05 kernel (pipeline
+# fill, TMEM allocation, a separate split launch) took 18 us against 15 us for the library's SIMT product, and its weight-gradient
+# twin 31 us against 10 us -- node tables (>= 4096 rows) go to the tensor cores, relation tables stay with the library.
+_TC_MIN_ROWS = 4096
 
 
 def small_mm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
