@@ -177,19 +177,28 @@ int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, int64_t ldg
  * Completion scorer: TransE-L1 margin loss of JMAC.completion_loss (src/jmac_model.py:345-374)
  * on the reference's exact batch layout (train.py:347-352): M = (1+K)*B triples, positives are the
  * first B, the negative at flat position B + k*B + b is compared with positive b.
- *   score[l*M + m] = || ent_l[h_m] + rel_l[r_m] - ent_l[t_m] ||_1          (saved for backward)
+ *   score[l*M + m] = || ent_l[h_m] + rel_l[r_m] - ent_l[t_m] ||_1          (optional output, may be NULL)
  *   loss[l]        = mean_{b,k} max(score_b - score_{B+kB+b}, -margin) + margin
- * n_layers <= 4 tables are scored in one pass over the indices.
+ * n_layers <= 4 tables are scored in one pass over the indices.  h and r need NOT be tiled (any index lists of length M
+ * are accepted, as in the reference); the tiled layout is the fast case.
+ * `record` (NULL when no gradient is needed; jmac_transe_record_bytes bytes, 256-byte aligned) receives what backward
+ * needs: per triple d loss/d score up to the scale and the sign pattern of h + r - t (2 bits per feature), per positive the
+ * dense gradient row of its leading (h, r) run.  Backward never gathers an embedding row again.
  * ------------------------------------------------------------------------------------------ */
+size_t jmac_transe_record_bytes(int64_t M, int64_t B, int n_layers, int d);
 int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int n_layers, int d,
                            const int64_t* h, const int64_t* r, const int64_t* t, int64_t M,
                            int64_t B, int64_t n_ent, int64_t n_rel, float margin, float* score,
-                           float* loss, void* stream);
-/* ACCUMULATES into d_ent[l][n_ent,d], d_rel[l][n_rel,d] (caller zeroes): gloss[l] * dloss[l]/d. */
-int jmac_transe_margin_bwd(const float* const* ent, const float* const* rel, int n_layers, int d,
-                           const int64_t* h, const int64_t* r, const int64_t* t, int64_t M,
-                           int64_t B, int64_t n_ent, int64_t n_rel, float margin, const float* score,
-                           const float* gloss, float* const* d_ent, float* const* d_rel, void* stream);
+                           float* loss, void* record, void* stream);
+/* Atomics-free, bit-reproducible backward: WRITES the rows of d_ent[l][n_ent,d], d_rel[l][n_rel,d] that occur in the batch
+ * with gloss[l] * dloss[l]/d(row) (every such row exactly once); rows that do not occur are not touched (the caller provides
+ * zeroed tables).  The occurrences of every row are radix-sorted once per call (all layers share the indices) and reduced in
+ * a fixed order.  workspace: jmac_transe_bwd_workspace_bytes bytes, 256-byte aligned.  2*M + B < 2^30. */
+size_t jmac_transe_bwd_workspace_bytes(int64_t M, int64_t B, int n_layers, int d);
+int jmac_transe_margin_bwd(int n_layers, int d, const int64_t* h, const int64_t* r, const int64_t* t,
+                           int64_t M, int64_t B, int64_t n_ent, int64_t n_rel, const void* record,
+                           const float* gloss, float* const* d_ent, float* const* d_rel,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pair cosine: cos[m] = <A[ia_m], B[ib_m]> / (max(|A[ia_m]|,1e-12) max(|B[ib_m]|,1e-12)), the

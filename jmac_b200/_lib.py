@@ -39,8 +39,10 @@ _SIGNATURES = {
     "jmac_gemm_tf32x3_add": (c_int, [P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, c_int64, P]),
     "jmac_gemm_tn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "jmac_gemm_tn_tf32x3": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, P, P]),
-    "jmac_transe_margin_fwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P]),
-    "jmac_transe_margin_bwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, P, P]),
+    "jmac_transe_record_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "jmac_transe_margin_fwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, P]),
+    "jmac_transe_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "jmac_transe_margin_bwd": (c_int, [c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, P, P, P, P, P, c_size_t, P]),
     "jmac_pair_cos_fwd": (c_int, [P, P, c_int, P, P, c_int64, c_int64, c_int64, P, P]),
     "jmac_pair_cos_bwd": (c_int, [P, P, c_int, P, P, c_int64, c_int64, c_int64, P, P, P, P]),
     "jmac_l1_dist": (c_int, [P, P, c_int, c_int, P, P, c_int64, c_int64, c_int64, c_int, P, P]),

@@ -4,12 +4,24 @@
 // the batch layout of train.py:347-352, and the F.normalize + row-dot of alignment_loss_simple /
 // alignment_loss (src/jmac_model.py:243-248, 268-287).
 //
-// One warp per positive b walks its K+1 triples m = k*B + b.  The (h, r) rows are reloaded only
+// Forward: one warp per positive b walks its K+1 triples m = k*B + b.  The (h, r) rows are reloaded only
 // when the index changes (they are tiled K+1 times in the reference layout), so the HBM traffic is
-// the algorithmic (K+3) rows per positive per layer.  Backward skips hinge-inactive negatives
-// entirely and scatters gradient rows with 128-bit vector REDs (the destination tables are dense
-// autograd gradients; collisions between random negatives are rare).
+// the algorithmic (K+3) rows per positive per layer.  When a gradient will be asked for, the same pass
+// records everything backward needs WITHOUT re-gathering a single embedding row:
+//   coef[l][m]  d loss / d score_m up to the scale: the number of active hinge terms for a positive, -1 / 0 for an
+//               active / inactive negative (the positive is the first triple of its warp, so activity is known on the fly);
+//   mask[l][m]  the sign pattern of h + r - t (two bits per feature: > 0, < 0; sign(0) = 0 like torch.abs' gradient);
+//   dhr[l][b]   sum_k coef_k sgn_k over the leading run of equal (h, r) of positive b (all K+1 triples in the reference
+//               layout): the dense gradient row that h_b and r_b receive from that run.
+// Backward is then an atomics-free, bit-reproducible segmented reduction: the occurrences of every table row -- tails
+// (mask records), heads / relations outside a leading run (mask records), one dense record per positive for its head and
+// its relation -- are radix-sorted by row id once per batch (all layers share the indices); warps reduce fixed chunks of
+// the sorted list, rows whose occurrences straddle chunks are finished by a second, ordered pass over per-chunk carry rows.
+// Every gradient row is written exactly once, by one warp, in a fixed order: no float REDs (round 1 used vector REDs: 8 GB of
+// read-modify-write at B = 65536, K = 64, and run-to-run differences in the last bits).
 #include <math.h>
+
+#include <cub/cub.cuh>
 
 #include "common.cuh"
 
@@ -32,7 +44,45 @@ struct TransEParams {
     const float* gloss;  // [n_layers]
     int64_t n_ent, n_rel;
     int* status;         // out-of-range index flag (common.cuh: status_words)
+    // record for the atomics-free backward (all null when no gradient is needed)
+    float* coef;         // [n_layers, M]
+    void* smask;         // [n_layers, M, 32 lanes] SMaskT: low half = "h+r-t > 0" bits of the lane's features, high half = "< 0" bits
+    float* dhr;          // [n_layers, B, d]
 };
+
+// sign pattern of a lane's 4*VPL features: VPL <= 2 -> 8 + 8 bits, else 16 + 16 bits
+template <int VPL> struct SMaskT { typedef uint16_t type; static constexpr int HALF = 8; };
+template <> struct SMaskT<3> { typedef uint32_t type; static constexpr int HALF = 16; };
+template <> struct SMaskT<4> { typedef uint32_t type; static constexpr int HALF = 16; };
+inline size_t transe_mask_bytes(int d) { return (((d / 4 + 31) / 32) <= 2) ? 64 : 128; }
+
+template <int VPL>
+__device__ __forceinline__ unsigned sign_bits(const Row<VPL>& a, const Row<VPL>& b) {
+    constexpr int H = SMaskT<VPL>::HALF;
+    unsigned m = 0u;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 dlt = a.v[i] - b.v[i];
+        m |= (dlt.x > 0.f ? 1u : 0u) << (4 * i) | (dlt.y > 0.f ? 1u : 0u) << (4 * i + 1) | (dlt.z > 0.f ? 1u : 0u) << (4 * i + 2) |
+             (dlt.w > 0.f ? 1u : 0u) << (4 * i + 3);
+        m |= (dlt.x < 0.f ? 1u : 0u) << (H + 4 * i) | (dlt.y < 0.f ? 1u : 0u) << (H + 4 * i + 1) | (dlt.z < 0.f ? 1u : 0u) << (H + 4 * i + 2) |
+             (dlt.w < 0.f ? 1u : 0u) << (H + 4 * i + 3);
+    }
+    return m;
+}
+// acc += c * sgn, sgn decoded from the lane's bits
+template <int VPL>
+__device__ __forceinline__ void add_signed(Row<VPL>& acc, float c, unsigned m) {
+    constexpr int H = SMaskT<VPL>::HALF;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const unsigned pb = m >> (4 * i), nb = m >> (H + 4 * i);
+        acc.v[i].x += ((pb & 1u) ? c : 0.f) - ((nb & 1u) ? c : 0.f);
+        acc.v[i].y += ((pb & 2u) ? c : 0.f) - ((nb & 2u) ? c : 0.f);
+        acc.v[i].z += ((pb & 4u) ? c : 0.f) - ((nb & 4u) ? c : 0.f);
+        acc.v[i].w += ((pb & 8u) ? c : 0.f) - ((nb & 8u) ? c : 0.f);
+    }
+}
 
 __global__ void fill_kernel(float* p, int n, float v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,8 +98,9 @@ __device__ __forceinline__ float l1_diff(const Row<VPL>& a, const Row<VPL>& b) {
     return s;
 }
 
-template <int VPL, int U>
-__global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
+template <int VPL, int U, bool SAVE>
+__global__ void __launch_bounds__(256, SAVE ? 2 : 3) transe_fwd_kernel(TransEParams p) {
+    typedef typename SMaskT<VPL>::type smask_t;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -61,10 +112,16 @@ __global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
         if (live) {
             const float* ent = p.ent[l];
             const float* rel = p.rel[l];
-            int hprev = -1, rprev = -1;                      // ids fit 31 bits (checked by the host): 32-bit keeps the kernel at 3 CTAs / SM
-            Row<VPL> hr;
+            smask_t* maskl = SAVE ? reinterpret_cast<smask_t*>(p.smask) + (size_t)l * p.M * 32 : nullptr;
+            float* coefl = SAVE ? p.coef + (size_t)l * p.M : nullptr;
+            int hprev = -1, rprev = -1, h0 = -1, r0 = -1;    // ids fit 31 bits (checked by the host): 32-bit keeps the register count down
+            bool in_lead = true;                             // still inside the leading run of triples that share (h, r) with the positive
+            Row<VPL> hr, dlead;
             hr.zero();
+            dlead.zero();
             float pos = 0.f;
+            unsigned m0 = 0u;
+            int n_act = 0;
             for (int kb = 0; kb < p.K1; kb += 32) {
                 const int cnt = min(32, p.K1 - kb);
                 int hv = 0, rv = 0, tv = 0;
@@ -74,7 +131,7 @@ __global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
                     rv = (int)safe_index(__ldg(p.r + m), p.n_rel, p.status);
                     tv = (int)safe_index(__ldg(p.t + m), p.n_ent, p.status);
                 }
-                float sc_keep = 0.f;
+                float sc_keep = 0.f, cf_keep = 0.f;
                 for (int k = 0; k < cnt; k += U) {
                     Row<VPL> tr[U];
                     int hh[U], rr[U];
@@ -97,14 +154,43 @@ __global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
                                 for (int i = 0; i < VPL; ++i) hr.v[i] = hrow.v[i] + rrow.v[i];
                                 hprev = hh[u]; rprev = rr[u];
                             }
+                            const bool first = kb + k + u == 0;
+                            if (first) { h0 = hh[u]; r0 = rr[u]; }
+                            if (hh[u] != h0 || rr[u] != r0) in_lead = false;
                             const float sc = warp_sum(l1_diff<VPL>(hr, tr[u]));
                             if (lane == k + u) sc_keep = sc;
-                            if (kb + k + u == 0) pos = sc;
-                            else lsum += fmaxf(pos - sc, -p.margin);
+                            unsigned bits = 0u;
+                            if (SAVE) {
+                                bits = sign_bits<VPL>(hr, tr[u]);
+                                maskl[((size_t)(kb + k + u) * p.B + b) * 32 + lane] = (smask_t)bits;
+                            }
+                            if (first) {
+                                pos = sc;
+                                m0 = bits;
+                            } else {
+                                lsum += fmaxf(pos - sc, -p.margin);
+                                if (SAVE) {
+                                    const bool active = pos - sc > -p.margin;      // warp-uniform
+                                    if (lane == k + u) cf_keep = active ? -1.f : 0.f;
+                                    if (active) {
+                                        ++n_act;
+                                        if (in_lead) add_signed<VPL>(dlead, -1.f, bits);
+                                    }
+                                }
+                            }
                         }
                     }
                 }
-                if (lane < cnt) p.score[(int64_t)l * p.M + (int64_t)(kb + lane) * p.B + b] = sc_keep;
+                if (lane < cnt) {
+                    const int64_t m = (int64_t)(kb + lane) * p.B + b;
+                    if (p.score) p.score[(int64_t)l * p.M + m] = sc_keep;
+                    if (SAVE && kb + lane > 0) coefl[m] = cf_keep;
+                }
+            }
+            if (SAVE) {
+                if (lane == 0) coefl[b] = (float)n_act;           // the positive (k = 0): one unit per active hinge term
+                add_signed<VPL>(dlead, (float)n_act, m0);
+                store_row<VPL>(dlead, p.dhr + (size_t)l * p.B * d4 * 4, b, d4, lane);
             }
         }
         if (lane == 0) block_loss[l][wib] = lsum;
@@ -118,76 +204,186 @@ __global__ void __launch_bounds__(256, 3) transe_fwd_kernel(TransEParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward: sorted occurrence lists + chunked segmented reduction (see the file header).
+// Occurrence value word: bit 31 = dense record (payload = positive b: the row dhr[l][b]); bit 30 = head / relation role (sign +1),
+// else tail role (sign -1); payload = triple position m.  Key = table row, or `sentinel` (one past the last row) for the
+// head / relation occurrences that the dense record of their positive already covers.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned OCC_DENSE = 0x80000000u, OCC_HR = 0x40000000u, OCC_PAYLOAD = 0x3fffffffu;
+
+// cover[b] = length of the leading run of triples k = 0.. that share (h, r) with the positive (K1 in the reference layout)
+__global__ void transe_cover_kernel(const int64_t* __restrict__ h, const int64_t* __restrict__ r, int64_t B, int K1, int* __restrict__ cover) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const int64_t h0 = h[b], r0 = r[b];
+    int first = K1;
+    for (int k = lane; k < K1 && first == K1; k += 32) {
+        if (h[(int64_t)k * B + b] != h0 || r[(int64_t)k * B + b] != r0) first = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(FULL, first, o));
+    if (lane == 0) cover[b] = first;
+}
+
+__global__ void transe_keys_kernel(const int64_t* __restrict__ h, const int64_t* __restrict__ r, const int64_t* __restrict__ t, int64_t M,
+                                   int64_t B, int64_t n_ent, int64_t n_rel, const int* __restrict__ cover, unsigned* __restrict__ ekeys,
+                                   unsigned* __restrict__ evals, unsigned* __restrict__ rkeys, unsigned* __restrict__ rvals) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t b = m % B, k = m / B;
+    const unsigned hh = (unsigned)safe_index(h[m], n_ent, nullptr), rr = (unsigned)safe_index(r[m], n_rel, nullptr),
+                   tt = (unsigned)safe_index(t[m], n_ent, nullptr);          // flagged by the forward kernel already
+    const bool covered = k < cover[b];
+    ekeys[m] = tt;                                       evals[m] = (unsigned)m;
+    ekeys[M + m] = covered ? (unsigned)n_ent : hh;       evals[M + m] = (unsigned)m | OCC_HR;
+    rkeys[m] = covered ? (unsigned)n_rel : rr;           rvals[m] = (unsigned)m | OCC_HR;
+    if (k == 0) {
+        ekeys[2 * M + b] = hh;                           evals[2 * M + b] = (unsigned)b | OCC_DENSE;
+        rkeys[M + b] = rr;                               rvals[M + b] = (unsigned)b | OCC_DENSE;
+    }
+}
+
+struct ReduceParams {
+    const unsigned* keys;     // sorted
+    const unsigned* vals;
+    int64_t n_occ;
+    unsigned sentinel;
+    int chunk;                // occurrences per warp (multiple of 32)
+    int n_layers, d4;
+    int64_t M, B;
+    const float* coef;        // [L, M]
+    const void* smask;        // [L, M, 32]
+    const float* dhr;         // [L, B, d]
+    const float* gloss;       // [L]
+    float inv_pairs;          // 1 / (B (K1 - 1))
+    float* out[MAX_LAYERS];   // gradient tables (zeroed by the caller)
+    float* carry;             // [L, n_chunks, 2, d]: slot 0 = partial of the run continuing FROM the previous chunk, slot 1 = INTO the next
+    int64_t n_chunks;
+};
+
+// Pass A: one warp per chunk of the sorted list.  Runs of equal keys inside the chunk are written to the table directly;
+// the (at most two) runs that touch a chunk boundary and continue beyond it leave their partial sums in the carry rows.
+template <int VPL>
+__global__ void __launch_bounds__(256) transe_reduce_kernel(ReduceParams p) {
+    typedef typename SMaskT<VPL>::type smask_t;
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (c >= p.n_chunks) return;
+    const int64_t base = c * p.chunk;
+    const int64_t end = min(p.n_occ, base + p.chunk);
+    const unsigned first_key = p.keys[base];
+    if (first_key == p.sentinel) return;
+    const unsigned prev_last = c > 0 ? p.keys[base - 1] : 0xffffffffu;
+    const unsigned next_first = end < p.n_occ ? p.keys[end] : 0xfffffffeu;
+    const int d4 = p.d4;
+    const size_t row_f = (size_t)d4 * 4;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const float gs = p.gloss[l] * p.inv_pairs;
+        const float* coefl = p.coef + (size_t)l * p.M;
+        const smask_t* maskl = reinterpret_cast<const smask_t*>(p.smask) + (size_t)l * p.M * 32;
+        const float* dhrl = p.dhr + (size_t)l * p.B * row_f;
+        float* carry = p.carry + ((size_t)l * p.n_chunks + c) * 2 * row_f;
+        Row<VPL> acc;
+        acc.zero();
+        unsigned run_key = first_key;
+        bool run_from_start = true;                        // the current run began at the first occurrence of the chunk
+        for (int64_t b0 = base; b0 < end; b0 += 32) {
+            const int cnt = (int)min((int64_t)32, end - b0);
+            unsigned kv = p.sentinel, vv = 0u;
+            float cv = 0.f;
+            if (lane < cnt) {
+                kv = p.keys[b0 + lane];
+                vv = p.vals[b0 + lane];
+                if (kv != p.sentinel && !(vv & OCC_DENSE)) cv = coefl[vv & OCC_PAYLOAD];
+            }
+            for (int i = 0; i < cnt; ++i) {
+                const unsigned ki = __shfl_sync(FULL, kv, i);
+                if (ki == p.sentinel) break;               // warp-uniform; the sentinels sort to the end
+                if (ki != run_key) {
+                    // the finished run lies inside the chunk unless it began at the chunk start AND continues the previous chunk
+                    if (run_from_start && run_key == prev_last) store_row<VPL>(acc, carry, 0, d4, lane);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < VPL; ++q) acc.v[q] = gs * acc.v[q];
+                        store_row<VPL>(acc, p.out[l], run_key, d4, lane);
+                    }
+                    acc.zero();
+                    run_key = ki;
+                    run_from_start = false;
+                }
+                const unsigned vi = __shfl_sync(FULL, vv, i);
+                if (vi & OCC_DENSE) {
+                    Row<VPL> dr;
+                    load_row<VPL, true>(dr, dhrl, vi & OCC_PAYLOAD, d4, lane);
+#pragma unroll
+                    for (int q = 0; q < VPL; ++q) acc.v[q] = acc.v[q] + dr.v[q];
+                } else {
+                    const float ci = __shfl_sync(FULL, cv, i);
+                    if (ci != 0.f) {                       // inactive negatives cost nothing (warp-uniform)
+                        const unsigned bits = (unsigned)maskl[(size_t)(vi & OCC_PAYLOAD) * 32 + lane];
+                        add_signed<VPL>(acc, (vi & OCC_HR) ? ci : -ci, bits);
+                    }
+                }
+            }
+        }
+        // the last run of the chunk
+        const bool head = run_from_start && run_key == prev_last;
+        const bool tail = run_key == next_first;
+        if (head) store_row<VPL>(acc, carry, 0, d4, lane);             // (head && tail: the whole chunk is one through-run, slot 0)
+        else if (tail) store_row<VPL>(acc, carry, 1, d4, lane);
+        else {
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) acc.v[q] = gs * acc.v[q];
+            store_row<VPL>(acc, p.out[l], run_key, d4, lane);
+        }
+    }
+}
+
+// Pass B: the chunk in which a multi-chunk run STARTS finishes it: its own tail partial plus the head partials of the following
+// chunks, in list order, while they continue the same key.
+template <int VPL>
+__global__ void __launch_bounds__(256) transe_fixup_kernel(ReduceParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (c >= p.n_chunks) return;
+    const int64_t base = c * p.chunk;
+    const int64_t end = min(p.n_occ, base + p.chunk);
+    if (end >= p.n_occ) return;                               // no next chunk: nothing continues
+    const unsigned key = p.keys[end - 1];                     // last key of this chunk
+    if (key == p.sentinel || p.keys[end] != key) return;      // its last run does not continue
+    // does the run start in this chunk?  Not if the whole chunk is that key and it already continued the previous chunk.
+    if (p.keys[base] == key && c > 0 && p.keys[base - 1] == key) return;
+    const int d4 = p.d4;
+    const size_t row_f = (size_t)d4 * 4;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const float gs = p.gloss[l] * p.inv_pairs;
+        const float* carry_l = p.carry + (size_t)l * p.n_chunks * 2 * row_f;
+        Row<VPL> acc;
+        load_row<VPL, true>(acc, carry_l + (size_t)c * 2 * row_f, 1, d4, lane);
+        for (int64_t c2 = c + 1; c2 < p.n_chunks; ++c2) {
+            const int64_t b2 = c2 * p.chunk, e2 = min(p.n_occ, b2 + p.chunk);
+            if (p.keys[b2] != key) break;
+            Row<VPL> part;
+            load_row<VPL, true>(part, carry_l + (size_t)c2 * 2 * row_f, 0, d4, lane);
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) acc.v[q] = acc.v[q] + part.v[q];
+            const bool through = p.keys[e2 - 1] == key && e2 < p.n_occ && p.keys[e2] == key;
+            if (!through) break;
+        }
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) acc.v[q] = gs * acc.v[q];
+        store_row<VPL>(acc, p.out[l], key, d4, lane);
+    }
+}
+
 template <int VPL>
 __device__ __forceinline__ void red_row(float* base, int64_t row, int d4, int lane, const Row<VPL>& v) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const int c = i * 32 + lane;
         if (c < d4) red_add_v4(base + (row * d4 + c) * 4, v.v[i]);
-    }
-}
-
-__device__ __forceinline__ float sgn(float v) { return (v > 0.f ? 1.f : 0.f) - (v < 0.f ? 1.f : 0.f); }
-
-template <int VPL>
-__global__ void __launch_bounds__(256) transe_bwd_kernel(TransEParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= p.B) return;
-    const int d4 = p.d4;
-    for (int l = 0; l < p.n_layers; ++l) {
-        const float* ent = p.ent[l];
-        const float* rel = p.rel[l];
-        const float* score = p.score + (int64_t)l * p.M;
-        const float gs = p.gloss[l] / ((float)p.B * (float)(p.K1 - 1));
-        const float pos = score[b];
-        // pass 1: number of active hinge terms of this positive
-        int act = 0;
-        for (int k = 1 + lane; k < p.K1; k += 32) act += (pos - score[(int64_t)k * p.B + b] > -p.margin) ? 1 : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) act += __shfl_xor_sync(FULL, act, o);
-        int64_t hprev = -1, rprev = -1;
-        Row<VPL> hr, dhr;
-        hr.zero(); dhr.zero();
-        bool dirty = false;
-        for (int k = 0; k < p.K1; ++k) {
-            const int64_t m = (int64_t)k * p.B + b;
-            float ds;
-            if (k == 0) ds = gs * (float)act;
-            else ds = (pos - score[m] > -p.margin) ? -gs : 0.f;
-            if (ds == 0.f) continue;  // warp-uniform: inactive negatives cost no row traffic
-            const int64_t hh = safe_index(__ldg(p.h + m), p.n_ent, p.status), rr = safe_index(__ldg(p.r + m), p.n_rel, p.status),
-                          tt = safe_index(__ldg(p.t + m), p.n_ent, p.status);
-            Row<VPL> tr;
-            load_row<VPL, true>(tr, ent, tt, d4, lane);
-            if (hh != hprev || rr != rprev) {
-                if (dirty) {
-                    red_row<VPL>(p.d_ent[l], hprev, d4, lane, dhr);
-                    red_row<VPL>(p.d_rel[l], rprev, d4, lane, dhr);
-                    dhr.zero();
-                    dirty = false;
-                }
-                Row<VPL> hrow, rrow;
-                load_row<VPL, true>(hrow, ent, hh, d4, lane);
-                load_row<VPL, false>(rrow, rel, rr, d4, lane);
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) hr.v[i] = hrow.v[i] + rrow.v[i];
-                hprev = hh; rprev = rr;
-            }
-            Row<VPL> dt;
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                const float4 s4 = make_float4(sgn(hr.v[i].x - tr.v[i].x), sgn(hr.v[i].y - tr.v[i].y), sgn(hr.v[i].z - tr.v[i].z), sgn(hr.v[i].w - tr.v[i].w));
-                fma4(dhr.v[i], ds, s4);
-                dt.v[i] = (-ds) * s4;
-            }
-            dirty = true;
-            red_row<VPL>(p.d_ent[l], tt, d4, lane, dt);
-        }
-        if (dirty) {
-            red_row<VPL>(p.d_ent[l], hprev, d4, lane, dhr);
-            red_row<VPL>(p.d_rel[l], rprev, d4, lane, dhr);
-        }
     }
 }
 
@@ -268,17 +464,87 @@ static int fill_transe(TransEParams& p, const float* const* ent, const float* co
     p.score = nullptr; p.loss = nullptr; p.gloss = nullptr;
     JMAC_ARG(n_ent > 0 && n_ent < (int64_t(1) << 31) && n_rel > 0 && n_rel < (int64_t(1) << 31));      // the kernels keep ids in 32 bits
     p.n_ent = n_ent; p.n_rel = n_rel; p.status = status_words() ? status_words() + JMAC_ST_TRIPLE : nullptr;
+    p.coef = nullptr; p.smask = nullptr; p.dhr = nullptr;
     return 0;
+}
+
+static int bits_for_u(uint64_t n) {  // bits needed to represent values in [0, n]
+    int b = 1;
+    while ((uint64_t(1) << b) <= n) ++b;
+    return b;
+}
+
+// occurrences per warp of the reduction: 32 on small batches (more warps), 128 on large ones (fewer carry rows)
+static int reduce_chunk(int64_t n_occ) { return n_occ >= (int64_t(1) << 20) ? 128 : 32; }
+
+struct TransEBwdLayout {
+    size_t off_cover, off_ekeys, off_evals, off_ekeys2, off_evals2, off_rkeys, off_rvals, off_rkeys2, off_rvals2, off_carry, off_cub, total;
+    size_t cub_bytes;
+    int64_t n_eocc, n_rocc, e_chunks, r_chunks;
+    int e_chunk, r_chunk;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static TransEBwdLayout transe_bwd_layout(int64_t M, int64_t B, int n_layers, int d) {
+    TransEBwdLayout L;
+    L.n_eocc = 2 * M + B;
+    L.n_rocc = M + B;
+    L.e_chunk = reduce_chunk(L.n_eocc);
+    L.r_chunk = reduce_chunk(L.n_rocc);
+    L.e_chunks = (L.n_eocc + L.e_chunk - 1) / L.e_chunk;
+    L.r_chunks = (L.n_rocc + L.r_chunk - 1) / L.r_chunk;
+    size_t o = 0;
+    L.off_cover = o;  o += align256(sizeof(int) * (size_t)B);
+    L.off_ekeys = o;  o += align256(4 * (size_t)L.n_eocc);
+    L.off_evals = o;  o += align256(4 * (size_t)L.n_eocc);
+    L.off_ekeys2 = o; o += align256(4 * (size_t)L.n_eocc);
+    L.off_evals2 = o; o += align256(4 * (size_t)L.n_eocc);
+    L.off_rkeys = o;  o += align256(4 * (size_t)L.n_rocc);
+    L.off_rvals = o;  o += align256(4 * (size_t)L.n_rocc);
+    L.off_rkeys2 = o; o += align256(4 * (size_t)L.n_rocc);
+    L.off_rvals2 = o; o += align256(4 * (size_t)L.n_rocc);
+    const int64_t max_chunks = L.e_chunks > L.r_chunks ? L.e_chunks : L.r_chunks;      // the carry rows are reused by the two reductions
+    L.off_carry = o;  o += align256(sizeof(float) * (size_t)n_layers * (size_t)max_chunks * 2 * (size_t)d);
+    size_t c1 = 0, c2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, c1, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                    (int)L.n_eocc, 0, 32);
+    cub::DeviceRadixSort::SortPairs(nullptr, c2, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                    (int)L.n_rocc, 0, 32);
+    L.cub_bytes = c1 > c2 ? c1 : c2;
+    L.off_cub = o;    o += align256(L.cub_bytes);
+    L.total = o;
+    return L;
+}
+
+extern "C" size_t jmac_transe_record_bytes(int64_t M, int64_t B, int n_layers, int d) {
+    if (M <= 0 || B <= 0 || n_layers <= 0 || !dim_ok(d)) return 0;
+    // coef [L,M] f32 | mask [L,M,64|128 B] | dhr [L,B,d] f32, each 256-byte aligned
+    return align256(4 * (size_t)n_layers * M) + align256(transe_mask_bytes(d) * (size_t)n_layers * M) + align256(4 * (size_t)n_layers * B * d);
+}
+
+extern "C" size_t jmac_transe_bwd_workspace_bytes(int64_t M, int64_t B, int n_layers, int d) {
+    if (M <= 0 || B <= 0 || n_layers <= 0 || !dim_ok(d) || 2 * M + B >= (int64_t(1) << 30)) return 0;
+    return transe_bwd_layout(M, B, n_layers, d).total;
+}
+
+static void transe_record_ptrs(TransEParams& p, void* record, int d) {
+    char* w = reinterpret_cast<char*>(record);
+    p.coef = reinterpret_cast<float*>(w);  w += align256(4 * (size_t)p.n_layers * p.M);
+    p.smask = w;                           w += align256(transe_mask_bytes(d) * (size_t)p.n_layers * p.M);
+    p.dhr = reinterpret_cast<float*>(w);
 }
 
 extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
                                       const int64_t* r, const int64_t* t, int64_t M, int64_t B, int64_t n_ent, int64_t n_rel,
-                                      float margin, float* score, float* loss, void* stream) {
+                                      float margin, float* score, float* loss, void* record, void* stream) {
     TransEParams p;
     int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, n_ent, n_rel, margin);
     if (rc) return rc;
-    JMAC_ARG(score && loss);
+    JMAC_ARG(loss != nullptr);
+    JMAC_ARG((reinterpret_cast<uintptr_t>(record) & 255) == 0);
     p.score = score; p.loss = loss;
+    if (record) transe_record_ptrs(p, record, d);
     cudaStream_t st = (cudaStream_t)stream;
     fill_kernel<<<1, 32, 0, st>>>(loss, n_layers, margin);
     JMAC_LAUNCH_CHECK();
@@ -286,28 +552,67 @@ extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* cons
     const int64_t blocks = (B + 7) / 8;
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL <= 2 ? 4 : 2;
-        transe_fwd_kernel<VPL, U><<<(unsigned)blocks, threads, 0, st>>>(p);
+        if (record) transe_fwd_kernel<VPL, U, true><<<(unsigned)blocks, threads, 0, st>>>(p);
+        else transe_fwd_kernel<VPL, U, false><<<(unsigned)blocks, threads, 0, st>>>(p);
     });
     JMAC_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int jmac_transe_margin_bwd(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
-                                      const int64_t* r, const int64_t* t, int64_t M, int64_t B, int64_t n_ent, int64_t n_rel, float margin,
-                                      const float* score, const float* gloss, float* const* d_ent, float* const* d_rel, void* stream) {
-    TransEParams p;
-    int rc = fill_transe(p, ent, rel, n_layers, d, h, r, t, M, B, n_ent, n_rel, margin);
-    if (rc) return rc;
-    JMAC_ARG(score && gloss && d_ent && d_rel);
-    for (int l = 0; l < n_layers; ++l) {
-        JMAC_ARG(d_ent[l] && d_rel[l]);
-        p.d_ent[l] = d_ent[l]; p.d_rel[l] = d_rel[l];
-    }
-    p.score = const_cast<float*>(score); p.gloss = gloss;
-    const int threads = 256;
-    const int64_t blocks = (B + 7) / 8;
-    JMAC_DISPATCH_VPL(d, { transe_bwd_kernel<VPL><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(p); });
+extern "C" int jmac_transe_margin_bwd(int n_layers, int d, const int64_t* h, const int64_t* r, const int64_t* t, int64_t M, int64_t B,
+                                      int64_t n_ent, int64_t n_rel, const void* record, const float* gloss, float* const* d_ent,
+                                      float* const* d_rel, void* workspace, size_t workspace_bytes, void* stream) {
+    JMAC_ARG(h && r && t && record && gloss && d_ent && d_rel && workspace);
+    JMAC_ARG(n_layers >= 1 && n_layers <= MAX_LAYERS && dim_ok(d));
+    JMAC_ARG(B > 0 && M >= 2 * B && (M % B) == 0 && M / B < (1 << 20) && 2 * M + B < (int64_t(1) << 30));
+    JMAC_ARG(n_ent > 0 && n_ent < (int64_t(1) << 31) - 1 && n_rel > 0 && n_rel < (int64_t(1) << 31) - 1);
+    JMAC_ARG((reinterpret_cast<uintptr_t>(record) & 255) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+    const TransEBwdLayout L = transe_bwd_layout(M, B, n_layers, d);
+    JMAC_ARG(workspace_bytes >= L.total);
+    for (int l = 0; l < n_layers; ++l) JMAC_ARG(d_ent[l] && d_rel[l]);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = reinterpret_cast<char*>(workspace);
+    int* cover = reinterpret_cast<int*>(w + L.off_cover);
+    unsigned* ekeys = reinterpret_cast<unsigned*>(w + L.off_ekeys);   unsigned* evals = reinterpret_cast<unsigned*>(w + L.off_evals);
+    unsigned* ekeys2 = reinterpret_cast<unsigned*>(w + L.off_ekeys2); unsigned* evals2 = reinterpret_cast<unsigned*>(w + L.off_evals2);
+    unsigned* rkeys = reinterpret_cast<unsigned*>(w + L.off_rkeys);   unsigned* rvals = reinterpret_cast<unsigned*>(w + L.off_rvals);
+    unsigned* rkeys2 = reinterpret_cast<unsigned*>(w + L.off_rkeys2); unsigned* rvals2 = reinterpret_cast<unsigned*>(w + L.off_rvals2);
+    const int K1 = (int)(M / B);
+    transe_cover_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, st>>>(h, r, B, K1, cover);
     JMAC_LAUNCH_CHECK();
+    transe_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(h, r, t, M, B, n_ent, n_rel, cover, ekeys, evals, rkeys, rvals);
+    JMAC_LAUNCH_CHECK();
+    size_t cub_bytes = L.cub_bytes;
+    JMAC_CUDA(cub::DeviceRadixSort::SortPairs(w + L.off_cub, cub_bytes, ekeys, ekeys2, evals, evals2, (int)L.n_eocc, 0, bits_for_u((uint64_t)n_ent), st));
+    cub_bytes = L.cub_bytes;
+    JMAC_CUDA(cub::DeviceRadixSort::SortPairs(w + L.off_cub, cub_bytes, rkeys, rkeys2, rvals, rvals2, (int)L.n_rocc, 0, bits_for_u((uint64_t)n_rel), st));
+    ReduceParams q;
+    q.n_layers = n_layers; q.d4 = d / 4; q.M = M; q.B = B;
+    {
+        const char* rw = reinterpret_cast<const char*>(record);
+        q.coef = reinterpret_cast<const float*>(rw);  rw += align256(4 * (size_t)n_layers * M);
+        q.smask = rw;                                 rw += align256(transe_mask_bytes(d) * (size_t)n_layers * M);
+        q.dhr = reinterpret_cast<const float*>(rw);
+    }
+    q.gloss = gloss;
+    q.inv_pairs = 1.f / ((float)B * (float)(K1 - 1));
+    q.carry = reinterpret_cast<float*>(w + L.off_carry);
+    for (int l = 0; l < MAX_LAYERS; ++l) q.out[l] = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: entity tables (tails, uncovered heads, one dense record per positive); pass 1: relation tables
+        q.keys = pass == 0 ? ekeys2 : rkeys2;
+        q.vals = pass == 0 ? evals2 : rvals2;
+        q.n_occ = pass == 0 ? L.n_eocc : L.n_rocc;
+        q.sentinel = (unsigned)(pass == 0 ? n_ent : n_rel);
+        q.chunk = pass == 0 ? L.e_chunk : L.r_chunk;
+        q.n_chunks = pass == 0 ? L.e_chunks : L.r_chunks;
+        for (int l = 0; l < n_layers; ++l) q.out[l] = pass == 0 ? d_ent[l] : d_rel[l];
+        const unsigned blocks = (unsigned)((q.n_chunks * 32 + 255) / 256);
+        JMAC_DISPATCH_VPL(d, { transe_reduce_kernel<VPL><<<blocks, 256, 0, st>>>(q); });
+        JMAC_LAUNCH_CHECK();
+        JMAC_DISPATCH_VPL(d, { transe_fixup_kernel<VPL><<<blocks, 256, 0, st>>>(q); });
+        JMAC_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -527,7 +527,9 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
 
 
 class TransEMarginFn(torch.autograd.Function):
-    """loss[l] of include/jmac_b200.h:jmac_transe_margin_fwd for n_layers (ent, rel) table pairs."""
+    """loss[l] of include/jmac_b200.h:jmac_transe_margin_fwd for n_layers (ent, rel) table pairs.
+    Backward is an atomics-free segmented reduction over the radix-sorted occurrences of every table row
+    (csrc/scorer.cu): the dense gradient tables are bit-identical from run to run."""
 
     @staticmethod
     def forward(ctx, h, r, t, batch_size: int, margin: float, *tables):
@@ -549,31 +551,35 @@ class TransEMarginFn(torch.autograd.Function):
             # same failure the reference hits in score.view(-1, batch_size) (src/jmac_model.py:358,367)
             raise RuntimeError(f"shape '[-1, {B}]' is invalid for input of size {M - B}")
         _lib.raise_if_flagged()
-        score = torch.empty(n_layers * M, dtype=torch.float32, device=dev)
         loss = torch.empty(n_layers, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad)
+        record = None
+        if need_grad:
+            record = torch.empty(int(lib.jmac_transe_record_bytes(M, B, n_layers, d)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(lib.jmac_transe_margin_fwd(_ptr_array(ents), _ptr_array(rels), n_layers, d, ptr(h), ptr(r), ptr(t), M, B,
-                                             ents[0].shape[0], rels[0].shape[0], float(margin), ptr(score), ptr(loss), stream_ptr()),
+                                             ents[0].shape[0], rels[0].shape[0], float(margin), None, ptr(loss), ptr(record), stream_ptr()),
                   "jmac_transe_margin_fwd")
-        ctx.save_for_backward(h, r, t, score, *ents, *rels)
-        ctx.meta = (n_layers, d, M, B, float(margin))
+        if need_grad:
+            ctx.save_for_backward(h, r, t, record)
+        ctx.meta = (n_layers, d, M, B, tuple(ents[0].shape), tuple(rels[0].shape), dev)
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
         lib = _lib.load()
-        n_layers, d, M, B, margin = ctx.meta
-        h, r, t, score = ctx.saved_tensors[:4]
-        ents = list(ctx.saved_tensors[4:4 + n_layers])
-        rels = list(ctx.saved_tensors[4 + n_layers:])
-        dev = ents[0].device
+        n_layers, d, M, B, eshape, rshape, dev = ctx.meta
+        h, r, t, record = ctx.saved_tensors
         gloss = _f32c(gloss)
-        d_ents = [torch.zeros_like(x) for x in ents]
-        d_rels = [torch.zeros_like(x) for x in rels]
+        d_ents = [torch.zeros(eshape, dtype=torch.float32, device=dev) for _ in range(n_layers)]
+        d_rels = [torch.zeros(rshape, dtype=torch.float32, device=dev) for _ in range(n_layers)]
+        ws_bytes = int(lib.jmac_transe_bwd_workspace_bytes(M, B, n_layers, d))
+        if ws_bytes == 0:
+            raise _lib.JmacError("batch too large for the 30-bit occurrence words of the scorer's backward (2*M + B < 2^30)")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            check(lib.jmac_transe_margin_bwd(_ptr_array(ents), _ptr_array(rels), n_layers, d, ptr(h), ptr(r), ptr(t), M, B,
-                                             ents[0].shape[0], rels[0].shape[0], margin,
-                                             ptr(score), ptr(gloss), _ptr_array(d_ents), _ptr_array(d_rels), stream_ptr()),
+            check(lib.jmac_transe_margin_bwd(n_layers, d, ptr(h), ptr(r), ptr(t), M, B, eshape[0], rshape[0], ptr(record), ptr(gloss),
+                                             _ptr_array(d_ents), _ptr_array(d_rels), ptr(ws), ws_bytes, stream_ptr()),
                   "jmac_transe_margin_bwd")
         return (None, None, None, None, None, *d_ents, *d_rels)
 

