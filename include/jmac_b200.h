@@ -36,7 +36,8 @@ uint64_t jmac_launch_count(void);
 /* Asynchronous index errors.  The scorer / pair-cosine / link-prediction kernels take index lists straight from the caller
  * (the reference raises IndexError / a device-side assert on a bad one).  They never read or write out of bounds: an index
  * outside its table is replaced by row 0 and a flag is raised in mapped host memory.  jmac_status_poll returns and clears
- * the flags WITHOUT synchronising (bit 0: triple scorer h/r/t, bit 1: pair cosine ia/ib, bit 2: link prediction e/r/t/filter);
+ * the flags WITHOUT synchronising (bit 0: triple scorer h/r/t, bit 1: pair cosine ia/ib, bit 2: link prediction e/r/t/filter,
+ * bit 3: negative sampler: (h, r) out of range or fewer than k valid entities);
  * synchronise the stream first to be sure the kernels in question have run. */
 int jmac_status_poll(void);
 
@@ -199,6 +200,17 @@ int jmac_transe_margin_bwd(int n_layers, int d, const int64_t* h, const int64_t*
                            int64_t M, int64_t B, int64_t n_ent, int64_t n_rel, const void* record,
                            const float* gloss, float* const* d_ent, float* const* d_rel,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Filtered negative sampling: TrainDataset.get_neg_sample (modules/load/data_loader.py:36-47) for a whole batch on the
+ * device.  keys[n_keys]: the SORTED, unique int64 keys (h*n_rel + r)*n_ent + t of all known triples.  For every row b,
+ * out[b, 0..k) receives k DISTINCT entities drawn uniformly from those e with (h[b], r[b], e) not a known triple
+ * (sequential rejection of a Philox-4x32-10 stream keyed by (seed, b): the reference's distribution, not its stream).
+ * A row that cannot be filled (fewer than k valid entities, index out of range) raises status bit 3 (jmac_status_poll).
+ * ------------------------------------------------------------------------------------------ */
+int jmac_sample_negatives(const int64_t* keys, int64_t n_keys, const int64_t* h, const int64_t* r,
+                          int64_t B, int64_t n_ent, int64_t n_rel, int k, uint64_t seed, int64_t* out,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pair cosine: cos[m] = <A[ia_m], B[ib_m]> / (max(|A[ia_m]|,1e-12) max(|B[ib_m]|,1e-12)), the

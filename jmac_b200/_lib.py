@@ -43,6 +43,7 @@ _SIGNATURES = {
     "jmac_transe_margin_fwd": (c_int, [P, P, c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, P]),
     "jmac_transe_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "jmac_transe_margin_bwd": (c_int, [c_int, c_int, P, P, P, c_int64, c_int64, c_int64, c_int64, P, P, P, P, P, c_size_t, P]),
+    "jmac_sample_negatives": (c_int, [P, c_int64, P, P, c_int64, c_int64, c_int64, c_int, ctypes.c_uint64, P, P]),
     "jmac_pair_cos_fwd": (c_int, [P, P, c_int, P, P, c_int64, c_int64, c_int64, P, P]),
     "jmac_pair_cos_bwd": (c_int, [P, P, c_int, P, P, c_int64, c_int64, c_int64, P, P, P, P]),
     "jmac_l1_dist": (c_int, [P, P, c_int, c_int, P, P, c_int64, c_int64, c_int64, c_int, P, P]),
@@ -91,7 +92,8 @@ def check(rc: int, what: str = ""):
 
 
 _STATUS_WHAT = {0: "batch_h / batch_r / batch_t of the completion scorer", 1: "an index list of the pair-cosine (alignment) loss",
-                2: "e_index / r_index / target / filter list of link prediction"}
+                2: "e_index / r_index / target / filter list of link prediction",
+                3: "the negative sampler ((h, r) out of range, or fewer than k entities that are not known tails)"}
 
 
 def raise_if_flagged(sync: bool = False):

@@ -15,7 +15,7 @@ void count_launch();
 // word `which` when an index is out of range (and use row 0 instead, so nothing is read or written out of bounds);
 // jmac_status_poll() reads and clears them without synchronising anything.  nullptr if the allocation failed.
 int* status_words();
-enum { JMAC_ST_TRIPLE = 0, JMAC_ST_PAIR = 1, JMAC_ST_LINKPRED = 2, JMAC_ST_WORDS = 8 };
+enum { JMAC_ST_TRIPLE = 0, JMAC_ST_PAIR = 1, JMAC_ST_LINKPRED = 2, JMAC_ST_SAMPLER = 3, JMAC_ST_WORDS = 8 };
 
 #define JMAC_CUDA(expr)                                                                    \
     do {                                                                                   \

@@ -48,6 +48,7 @@ struct TransEParams {
     float* coef;         // [n_layers, M]
     void* smask;         // [n_layers, M, 32 lanes] SMaskT: low half = "h+r-t > 0" bits of the lane's features, high half = "< 0" bits
     float* dhr;          // [n_layers, B, d]
+    float* loss_part;    // [n_layers, gridDim.x]: per-block hinge sums, added up in a fixed order by transe_loss_kernel
 };
 
 // sign pattern of a lane's 4*VPL features: VPL <= 2 -> 8 + 8 bits, else 16 + 16 bits
@@ -82,11 +83,6 @@ __device__ __forceinline__ void add_signed(Row<VPL>& acc, float c, unsigned m) {
         acc.v[i].z += ((pb & 4u) ? c : 0.f) - ((nb & 4u) ? c : 0.f);
         acc.v[i].w += ((pb & 8u) ? c : 0.f) - ((nb & 8u) ? c : 0.f);
     }
-}
-
-__global__ void fill_kernel(float* p, int n, float v) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
 }
 
 template <int VPL>
@@ -199,9 +195,23 @@ __global__ void __launch_bounds__(256, SAVE ? 2 : 3) transe_fwd_kernel(TransEPar
     if (threadIdx.x < p.n_layers) {
         float s = 0.f;
         for (int w = 0; w < 8; ++w) s += block_loss[threadIdx.x][w];
-        const float inv = 1.f / ((float)p.B * (float)(p.K1 - 1));
-        atomicAdd(p.loss + threadIdx.x, s * inv);
+        p.loss_part[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
     }
+}
+
+// loss[l] = margin + (sum of the block partials, in a fixed order) / (B (K1 - 1)): one block per layer, bit-reproducible
+__global__ void __launch_bounds__(256) transe_loss_kernel(const float* __restrict__ part, int n_blocks, float margin, float inv, float* __restrict__ loss) {
+    __shared__ float sh[256];
+    const float* pl = part + (size_t)blockIdx.x * n_blocks;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n_blocks; i += 256) s += pl[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[blockIdx.x] = margin + sh[0] * inv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,7 +474,7 @@ static int fill_transe(TransEParams& p, const float* const* ent, const float* co
     p.score = nullptr; p.loss = nullptr; p.gloss = nullptr;
     JMAC_ARG(n_ent > 0 && n_ent < (int64_t(1) << 31) && n_rel > 0 && n_rel < (int64_t(1) << 31));      // the kernels keep ids in 32 bits
     p.n_ent = n_ent; p.n_rel = n_rel; p.status = status_words() ? status_words() + JMAC_ST_TRIPLE : nullptr;
-    p.coef = nullptr; p.smask = nullptr; p.dhr = nullptr;
+    p.coef = nullptr; p.smask = nullptr; p.dhr = nullptr; p.loss_part = nullptr;
     return 0;
 }
 
@@ -519,8 +529,9 @@ static TransEBwdLayout transe_bwd_layout(int64_t M, int64_t B, int n_layers, int
 
 extern "C" size_t jmac_transe_record_bytes(int64_t M, int64_t B, int n_layers, int d) {
     if (M <= 0 || B <= 0 || n_layers <= 0 || !dim_ok(d)) return 0;
-    // coef [L,M] f32 | mask [L,M,64|128 B] | dhr [L,B,d] f32, each 256-byte aligned
-    return align256(4 * (size_t)n_layers * M) + align256(transe_mask_bytes(d) * (size_t)n_layers * M) + align256(4 * (size_t)n_layers * B * d);
+    // coef [L,M] f32 | mask [L,M,64|128 B] | dhr [L,B,d] f32 | per-block loss partials [L, ceil(B/8)] f32, each 256-byte aligned
+    return align256(4 * (size_t)n_layers * M) + align256(transe_mask_bytes(d) * (size_t)n_layers * M) + align256(4 * (size_t)n_layers * B * d) +
+           align256(4 * (size_t)n_layers * ((B + 7) / 8));
 }
 
 extern "C" size_t jmac_transe_bwd_workspace_bytes(int64_t M, int64_t B, int n_layers, int d) {
@@ -532,7 +543,8 @@ static void transe_record_ptrs(TransEParams& p, void* record, int d) {
     char* w = reinterpret_cast<char*>(record);
     p.coef = reinterpret_cast<float*>(w);  w += align256(4 * (size_t)p.n_layers * p.M);
     p.smask = w;                           w += align256(transe_mask_bytes(d) * (size_t)p.n_layers * p.M);
-    p.dhr = reinterpret_cast<float*>(w);
+    p.dhr = reinterpret_cast<float*>(w);   w += align256(4 * (size_t)p.n_layers * p.B * (size_t)d);
+    p.loss_part = reinterpret_cast<float*>(w);
 }
 
 extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* const* rel, int n_layers, int d, const int64_t* h,
@@ -544,18 +556,24 @@ extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* cons
     JMAC_ARG(loss != nullptr);
     JMAC_ARG((reinterpret_cast<uintptr_t>(record) & 255) == 0);
     p.score = score; p.loss = loss;
-    if (record) transe_record_ptrs(p, record, d);
     cudaStream_t st = (cudaStream_t)stream;
-    fill_kernel<<<1, 32, 0, st>>>(loss, n_layers, margin);
-    JMAC_LAUNCH_CHECK();
     const int threads = 256;
     const int64_t blocks = (B + 7) / 8;
+    float* part_tmp = nullptr;
+    if (record) transe_record_ptrs(p, record, d);
+    else {                                                   // no record buffer to host the loss partials: stream-ordered scratch
+        JMAC_CUDA(cudaMallocAsync(&part_tmp, sizeof(float) * (size_t)n_layers * (size_t)blocks, st));
+        p.loss_part = part_tmp;
+    }
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL <= 2 ? 4 : 2;
         if (record) transe_fwd_kernel<VPL, U, true><<<(unsigned)blocks, threads, 0, st>>>(p);
         else transe_fwd_kernel<VPL, U, false><<<(unsigned)blocks, threads, 0, st>>>(p);
     });
     JMAC_LAUNCH_CHECK();
+    transe_loss_kernel<<<n_layers, 256, 0, st>>>(p.loss_part, (int)blocks, margin, 1.f / ((float)B * (float)(p.K1 - 1)), loss);
+    JMAC_LAUNCH_CHECK();
+    if (part_tmp) JMAC_CUDA(cudaFreeAsync(part_tmp, st));
     return 0;
 }
 

@@ -7,10 +7,13 @@ is why train.py runs it in 12 DataLoader workers (train.py:288-294).  Here a who
 device the indices live on: candidates are drawn i.i.d. uniform, candidates that are true tails or repeat an earlier
 candidate of the same row are rejected, and the first ``k`` survivors of every row are kept.  Sequential rejection of
 an i.i.d. uniform stream yields exactly the uniform distribution over ordered k-subsets of the valid entities, i.e.
-the reference's distribution; the random STREAM differs (torch Philox / MT instead of numpy's global generator), so
+the reference's distribution; the random STREAM differs (Philox instead of numpy's global generator), so
 parity is distributional -- the parity tests of the scorer feed precomputed negatives (north_star).
 
-Plain torch on integer tensors (plumbing, not a kernel): it runs wherever its inputs are.
+``sample_negatives`` is the CUDA kernel (csrc/sampling.cu: one thread per row, Philox-4x32-10 keyed by (seed, row), binary
+search in the sorted triple keys; one launch per batch, no host round trip besides the k-feasibility check).
+``sample_negatives_torch`` states the same procedure in batched torch ops; it is the host-side reference the CPU tests
+(validity, exhaustion, chi-square uniformity) exercise, and what the GPU test compares the kernel's distribution with.
 """
 from typing import Optional
 
@@ -67,10 +70,37 @@ def _first_occurrence(cand: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def sample_negatives(index: TripleIndex, h, r, k: int, generator: Optional[torch.Generator] = None, oversample: float = 1.5) -> torch.Tensor:
-    """[B, k] int64: for every (h[b], r[b]), k distinct entities drawn uniformly from those that are not known tails of
-    (h[b], r[b]) -- ``TrainDataset.get_neg_sample`` for a whole batch.  Raises if some (h, r) has fewer than k valid
-    entities (the reference's ``np.random.choice(..., replace=False)`` raises there too)."""
+def sample_negatives(index: TripleIndex, h, r, k: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """[B, k] int64 on the device: for every (h[b], r[b]), k distinct entities drawn uniformly from those that are not known
+    tails of (h[b], r[b]) -- ``TrainDataset.get_neg_sample`` for a whole batch, by the CUDA kernel ``jmac_sample_negatives``.
+    The stream is keyed by a 62-bit seed drawn from ``generator`` (default: torch's global CPU generator, so
+    ``torch.manual_seed`` makes it reproducible).  Raises ValueError if some (h, r) has fewer than k valid entities (the
+    reference's ``np.random.choice(..., replace=False)`` raises there too)."""
+    from . import _lib
+    from ._lib import check, ptr, stream_ptr
+    dev = index.device
+    if dev.type != "cuda":
+        raise _lib.JmacError("sample_negatives is a CUDA kernel; sample_negatives_torch is the host-side reference")
+    lib = _lib.load()
+    h = torch.as_tensor(h, device=dev).to(torch.int64).reshape(-1).contiguous()
+    r = torch.as_tensor(r, device=dev).to(torch.int64).reshape(-1).contiguous()
+    B, N = h.numel(), index.n_ent
+    out = torch.empty(B, k, dtype=torch.int64, device=dev)
+    if B == 0 or k == 0:
+        return out
+    if bool((N - index.n_true_tails(h, r) < k).any()):
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=generator.device if generator is not None else "cpu").item())
+    _lib.raise_if_flagged()
+    keys = index.keys.contiguous()
+    with torch.cuda.device(dev):
+        check(lib.jmac_sample_negatives(ptr(keys), int(keys.numel()), ptr(h), ptr(r), B, N, index.n_rel, int(k), seed, ptr(out), stream_ptr()),
+              "jmac_sample_negatives")
+    return out
+
+
+def sample_negatives_torch(index: TripleIndex, h, r, k: int, generator: Optional[torch.Generator] = None, oversample: float = 1.5) -> torch.Tensor:
+    """The same procedure in batched torch ops, wherever ``index`` lives (host-side reference, see the module docstring)."""
     dev = index.device
     h = torch.as_tensor(h, device=dev).to(torch.int64).reshape(-1)
     r = torch.as_tensor(r, device=dev).to(torch.int64).reshape(-1)

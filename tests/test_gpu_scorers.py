@@ -390,6 +390,41 @@ def test_negative_sampler_on_device_feeds_the_scorer():
                                  torch.cat((batch[:, 2], neg.t().reshape(-1))), B, 5.0)      # negatives [K, B] flattened: position B + k*B + b
     loss.sum().backward()
     assert torch.isfinite(loss).all() and ents[0].grad is not None
+    # reproducible under a seeded generator, different under another seed
+    again = sample_negatives(idx, batch[:, 0], batch[:, 1], K, generator=torch.Generator(device="cuda").manual_seed(1))
+    other = sample_negatives(idx, batch[:, 0], batch[:, 1], K, generator=torch.Generator(device="cuda").manual_seed(2))
+    assert torch.equal(neg, again) and not torch.equal(neg, other)
+
+
+def test_negative_sampler_kernel_is_uniform_and_exhaustive():
+    """The kernel's distribution: (a) with exactly k valid entities every row returns all of them; (b) chi-square test of
+    uniformity over the valid entities of one (h, r), against the same statistic of the torch reference procedure."""
+    import jmac_b200
+    from jmac_b200.sampling import TripleIndex, sample_negatives, sample_negatives_torch
+    n_ent, n_rel = 12, 2
+    tri = np.array([[0, 0, t] for t in range(9)] + [[1, 0, 5]])                       # (0,0) has 9 known tails: valid = {9, 10, 11}
+    idx = TripleIndex(tri, n_ent, n_rel, device="cuda")
+    neg = sample_negatives(idx, torch.tensor([0, 1, 0]), torch.tensor([0, 0, 0]), 3)
+    assert sorted(neg[0].tolist()) == [9, 10, 11] and sorted(neg[2].tolist()) == [9, 10, 11] and 5 not in neg[1].tolist()
+    with pytest.raises(ValueError):
+        sample_negatives(idx, torch.tensor([0]), torch.tensor([0]), 4)
+    assert sample_negatives(idx, torch.tensor([], dtype=torch.long), torch.tensor([], dtype=torch.long), 3).shape == (0, 3)
+    jmac_b200.check_errors()
+    # uniformity: 50 entities, 10 excluded, k = 4, 40000 rows -> every valid entity appears with probability k / 40
+    n_ent, k, B = 50, 4, 40000
+    tri = np.array([[0, 0, t] for t in range(10)])
+    idx = TripleIndex(tri, n_ent, 1, device="cuda")
+    z = torch.zeros(B, dtype=torch.long)
+    torch.manual_seed(7)
+    for fn in (sample_negatives, sample_negatives_torch):
+        neg = fn(idx, z, z, k)
+        cnt = torch.bincount(neg.reshape(-1).cpu(), minlength=n_ent).double()
+        assert float(cnt[:10].sum()) == 0
+        exp = B * k / 40.0
+        chi2 = float(((cnt[10:] - exp) ** 2 / exp).sum())
+        assert chi2 < 80.0, (fn.__name__, chi2)                                        # 39 degrees of freedom: P(chi2 > 80) ~ 1e-4
+        first = torch.bincount(neg[:, 0].cpu(), minlength=n_ent).double()[10:]        # the first pick alone is uniform too
+        assert float(((first - B / 40.0) ** 2 / (B / 40.0)).sum()) < 80.0
 
 
 def test_out_of_range_indices_are_flagged_not_followed():

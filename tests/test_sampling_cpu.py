@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from jmac_b200.sampling import TripleIndex, sample_negatives
+from jmac_b200.sampling import TripleIndex, sample_negatives_torch as sample_negatives
 
 
 def make_index(n_ent=50, n_rel=4, n_tri=300, seed=0):
