@@ -149,6 +149,14 @@ int jmac_bn_tanh_bwd_apply(const float* gout, const float* out, const float* pre
                            float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Row-wise L2 normalisation y = x / max(|x|_2, eps) (F.normalize of src/jmac_model.py:183,192,230-231) and its backward,
+ * one pass each.  inv[N] (may be NULL when no gradient is needed) keeps 1 / max(|x|, eps), negative where the clamp was active.
+ * ------------------------------------------------------------------------------------------ */
+int jmac_row_normalize_fwd(const float* x, int64_t N, int d, float eps, float* y, float* inv, void* stream);
+int jmac_row_normalize_bwd(const float* y, const float* inv, const float* g, int64_t N, int d, float* dx,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Node-level dense product with fp32 accuracy on the tensor cores (3xTF32 split, tcgen05):
  *   C[M,N] = A[M,K] . B[N,K]^T,  B given pre-split: B_hi = B with the low 13 mantissa bits cleared,
  *   B_lo = B - B_hi.  N % 32 == 0, N <= 256, K % 16 == 0; lda/ldb/ldc in elements (multiples of 4).

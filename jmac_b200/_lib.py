@@ -34,6 +34,8 @@ _SIGNATURES = {
     "jmac_bn_tanh_apply": (c_int, [P, c_int64, c_int, P, c_int64, P, P, P, P, c_float, c_float, c_int, P, P, P, P]),
     "jmac_bn_tanh_bwd_stats": (c_int, [P, P, P, c_int64, c_int, P, P, P, P]),
     "jmac_bn_tanh_bwd_apply": (c_int, [P, P, P, c_int64, c_int, P, P, P, P, c_int64, c_int, P, P, P, P]),
+    "jmac_row_normalize_fwd": (c_int, [P, c_int64, c_int, c_float, P, P, P]),
+    "jmac_row_normalize_bwd": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "jmac_split_tf32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P, P]),
     "jmac_gemm_tf32x3": (c_int, [P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
     "jmac_gemm_tf32x3_add": (c_int, [P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, c_int64, P]),

@@ -45,8 +45,8 @@ struct TransEParams {
     int64_t n_ent, n_rel;
     int* status;         // out-of-range index flag (common.cuh: status_words)
     // record for the atomics-free backward (all null when no gradient is needed)
-    float* coef;         // [n_layers, M]
-    void* smask;         // [n_layers, M, 32 lanes] SMaskT: low half = "h+r-t > 0" bits of the lane's features, high half = "< 0" bits
+    float* coef;         // [n_layers, B, K1]
+    void* smask;         // [n_layers, B, K1, 32 lanes] SMaskT: low half = "h+r-t > 0" bits of the lane's features, high half = "< 0" bits
     float* dhr;          // [n_layers, B, d]
     float* loss_part;    // [n_layers, gridDim.x]: per-block hinge sums, added up in a fixed order by transe_loss_kernel
 };
@@ -57,31 +57,60 @@ template <> struct SMaskT<3> { typedef uint32_t type; static constexpr int HALF 
 template <> struct SMaskT<4> { typedef uint32_t type; static constexpr int HALF = 16; };
 inline size_t transe_mask_bytes(int d) { return (((d / 4 + 31) / 32) <= 2) ? 64 : 128; }
 
+// Sign pattern of a - b for the lane's features: bit f of the low half = (a - b > 0), of the high half = (a - b < 0).
+// One funnel shift per feature collects the IEEE sign bits; exact zeros (sign(0) = 0, like torch.abs' gradient) are rare and are
+// found with one running min of |a - b| per lane, then patched on a slow path.
 template <int VPL>
 __device__ __forceinline__ unsigned sign_bits(const Row<VPL>& a, const Row<VPL>& b) {
     constexpr int H = SMaskT<VPL>::HALF;
-    unsigned m = 0u;
+    unsigned sg = 0u;
+    float mn = INFINITY;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
+    for (int i = VPL - 1; i >= 0; --i) {
         const float4 dlt = a.v[i] - b.v[i];
-        m |= (dlt.x > 0.f ? 1u : 0u) << (4 * i) | (dlt.y > 0.f ? 1u : 0u) << (4 * i + 1) | (dlt.z > 0.f ? 1u : 0u) << (4 * i + 2) |
-             (dlt.w > 0.f ? 1u : 0u) << (4 * i + 3);
-        m |= (dlt.x < 0.f ? 1u : 0u) << (H + 4 * i) | (dlt.y < 0.f ? 1u : 0u) << (H + 4 * i + 1) | (dlt.z < 0.f ? 1u : 0u) << (H + 4 * i + 2) |
-             (dlt.w < 0.f ? 1u : 0u) << (H + 4 * i + 3);
+        sg = __funnelshift_l(__float_as_uint(dlt.w), sg, 1);
+        sg = __funnelshift_l(__float_as_uint(dlt.z), sg, 1);
+        sg = __funnelshift_l(__float_as_uint(dlt.y), sg, 1);
+        sg = __funnelshift_l(__float_as_uint(dlt.x), sg, 1);
+        mn = fminf(mn, fminf(fminf(fabsf(dlt.x), fabsf(dlt.y)), fminf(fabsf(dlt.z), fabsf(dlt.w))));
     }
-    return m;
+    constexpr unsigned ALL = (1u << (4 * VPL)) - 1u;
+    unsigned nz = ALL;
+    if (mn == 0.f) {                                          // some feature of this lane is exactly zero
+        nz = 0u;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 dlt = a.v[i] - b.v[i];
+            nz |= (dlt.x != 0.f ? 1u : 0u) << (4 * i) | (dlt.y != 0.f ? 1u : 0u) << (4 * i + 1) | (dlt.z != 0.f ? 1u : 0u) << (4 * i + 2) |
+                  (dlt.w != 0.f ? 1u : 0u) << (4 * i + 3);
+        }
+    }
+    return ((~sg) & nz) | ((sg & nz) << H);
 }
 // acc += c * sgn, sgn decoded from the lane's bits
 template <int VPL>
 __device__ __forceinline__ void add_signed(Row<VPL>& acc, float c, unsigned m) {
     constexpr int H = SMaskT<VPL>::HALF;
+    constexpr unsigned ALL = (1u << (4 * VPL)) - 1u;
+    const unsigned pb = m & ALL, nb = (m >> H) & ALL;
+    if ((pb | nb) == ALL) {                                   // no exact zero in this lane's features (the common case): +c or -c
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const unsigned pb = m >> (4 * i), nb = m >> (H + 4 * i);
-        acc.v[i].x += ((pb & 1u) ? c : 0.f) - ((nb & 1u) ? c : 0.f);
-        acc.v[i].y += ((pb & 2u) ? c : 0.f) - ((nb & 2u) ? c : 0.f);
-        acc.v[i].z += ((pb & 4u) ? c : 0.f) - ((nb & 4u) ? c : 0.f);
-        acc.v[i].w += ((pb & 8u) ? c : 0.f) - ((nb & 8u) ? c : 0.f);
+        for (int i = 0; i < VPL; ++i) {
+            const unsigned q = nb >> (4 * i);
+            acc.v[i].x += (q & 1u) ? -c : c;
+            acc.v[i].y += (q & 2u) ? -c : c;
+            acc.v[i].z += (q & 4u) ? -c : c;
+            acc.v[i].w += (q & 8u) ? -c : c;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const unsigned p4 = pb >> (4 * i), n4 = nb >> (4 * i);
+            acc.v[i].x += ((p4 & 1u) ? c : 0.f) - ((n4 & 1u) ? c : 0.f);
+            acc.v[i].y += ((p4 & 2u) ? c : 0.f) - ((n4 & 2u) ? c : 0.f);
+            acc.v[i].z += ((p4 & 4u) ? c : 0.f) - ((n4 & 4u) ? c : 0.f);
+            acc.v[i].w += ((p4 & 8u) ? c : 0.f) - ((n4 & 8u) ? c : 0.f);
+        }
     }
 }
 
@@ -94,8 +123,8 @@ __device__ __forceinline__ float l1_diff(const Row<VPL>& a, const Row<VPL>& b) {
     return s;
 }
 
-template <int VPL, int U, bool SAVE>
-__global__ void __launch_bounds__(256, SAVE ? 2 : 3) transe_fwd_kernel(TransEParams p) {
+template <int VPL, int U, bool SAVE, int MINB>
+__global__ void __launch_bounds__(256, MINB) transe_fwd_kernel(TransEParams p) {
     typedef typename SMaskT<VPL>::type smask_t;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -108,8 +137,9 @@ __global__ void __launch_bounds__(256, SAVE ? 2 : 3) transe_fwd_kernel(TransEPar
         if (live) {
             const float* ent = p.ent[l];
             const float* rel = p.rel[l];
-            smask_t* maskl = SAVE ? reinterpret_cast<smask_t*>(p.smask) + (size_t)l * p.M * 32 : nullptr;
-            float* coefl = SAVE ? p.coef + (size_t)l * p.M : nullptr;
+            // record layout: [layer][positive b][k]: a warp writes its K1 coefficients / sign records contiguously
+            smask_t* maskl = SAVE ? reinterpret_cast<smask_t*>(p.smask) + ((size_t)l * p.M + (size_t)b * p.K1) * 32 : nullptr;
+            float* coefl = SAVE ? p.coef + (size_t)l * p.M + (size_t)b * p.K1 : nullptr;
             int hprev = -1, rprev = -1, h0 = -1, r0 = -1;    // ids fit 31 bits (checked by the host): 32-bit keeps the register count down
             bool in_lead = true;                             // still inside the leading run of triples that share (h, r) with the positive
             Row<VPL> hr, dlead;
@@ -158,7 +188,7 @@ __global__ void __launch_bounds__(256, SAVE ? 2 : 3) transe_fwd_kernel(TransEPar
                             unsigned bits = 0u;
                             if (SAVE) {
                                 bits = sign_bits<VPL>(hr, tr[u]);
-                                maskl[((size_t)(kb + k + u) * p.B + b) * 32 + lane] = (smask_t)bits;
+                                maskl[(size_t)(kb + k + u) * 32 + lane] = (smask_t)bits;
                             }
                             if (first) {
                                 pos = sc;
@@ -178,13 +208,12 @@ __global__ void __launch_bounds__(256, SAVE ? 2 : 3) transe_fwd_kernel(TransEPar
                     }
                 }
                 if (lane < cnt) {
-                    const int64_t m = (int64_t)(kb + lane) * p.B + b;
-                    if (p.score) p.score[(int64_t)l * p.M + m] = sc_keep;
-                    if (SAVE && kb + lane > 0) coefl[m] = cf_keep;
+                    if (p.score) p.score[(int64_t)l * p.M + (int64_t)(kb + lane) * p.B + b] = sc_keep;
+                    if (SAVE && kb + lane > 0) coefl[kb + lane] = cf_keep;
                 }
             }
             if (SAVE) {
-                if (lane == 0) coefl[b] = (float)n_act;           // the positive (k = 0): one unit per active hinge term
+                if (lane == 0) coefl[0] = (float)n_act;           // the positive (k = 0): one unit per active hinge term
                 add_signed<VPL>(dlead, (float)n_act, m0);
                 store_row<VPL>(dlead, p.dhr + (size_t)l * p.B * d4 * 4, b, d4, lane);
             }
@@ -261,21 +290,22 @@ struct ReduceParams {
     int64_t n_occ;
     unsigned sentinel;
     int chunk;                // occurrences per warp (multiple of 32)
-    int n_layers, d4;
+    int d4, K1;
     int64_t M, B;
-    const float* coef;        // [L, M]
-    const void* smask;        // [L, M, 32]
+    const float* coef;        // [L, B, K1]
+    const void* smask;        // [L, B, K1, 32]
     const float* dhr;         // [L, B, d]
     const float* gloss;       // [L]
     float inv_pairs;          // 1 / (B (K1 - 1))
     float* out[MAX_LAYERS];   // gradient tables (zeroed by the caller)
-    float* carry;             // [L, n_chunks, 2, d]: slot 0 = partial of the run continuing FROM the previous chunk, slot 1 = INTO the next
+    float* carry;             // [n_chunks, 2, L, d]: slot 0 = partial of the run continuing FROM the previous chunk, slot 1 = INTO the next
     int64_t n_chunks;
 };
 
-// Pass A: one warp per chunk of the sorted list.  Runs of equal keys inside the chunk are written to the table directly;
-// the (at most two) runs that touch a chunk boundary and continue beyond it leave their partial sums in the carry rows.
-template <int VPL>
+// Pass A: one warp per chunk of the sorted list, all NL layers in one walk (the index work is shared).  Runs of equal keys inside
+// the chunk are written to the tables directly; the (at most two) runs that touch a chunk boundary and continue beyond it leave
+// their partial sums in the carry rows.
+template <int VPL, int NL>
 __global__ void __launch_bounds__(256) transe_reduce_kernel(ReduceParams p) {
     typedef typename SMaskT<VPL>::type smask_t;
     const int lane = threadIdx.x & 31;
@@ -289,72 +319,98 @@ __global__ void __launch_bounds__(256) transe_reduce_kernel(ReduceParams p) {
     const unsigned next_first = end < p.n_occ ? p.keys[end] : 0xfffffffeu;
     const int d4 = p.d4;
     const size_t row_f = (size_t)d4 * 4;
-    for (int l = 0; l < p.n_layers; ++l) {
-        const float gs = p.gloss[l] * p.inv_pairs;
-        const float* coefl = p.coef + (size_t)l * p.M;
-        const smask_t* maskl = reinterpret_cast<const smask_t*>(p.smask) + (size_t)l * p.M * 32;
-        const float* dhrl = p.dhr + (size_t)l * p.B * row_f;
-        float* carry = p.carry + ((size_t)l * p.n_chunks + c) * 2 * row_f;
-        Row<VPL> acc;
-        acc.zero();
-        unsigned run_key = first_key;
-        bool run_from_start = true;                        // the current run began at the first occurrence of the chunk
-        for (int64_t b0 = base; b0 < end; b0 += 32) {
-            const int cnt = (int)min((int64_t)32, end - b0);
-            unsigned kv = p.sentinel, vv = 0u;
-            float cv = 0.f;
-            if (lane < cnt) {
-                kv = p.keys[b0 + lane];
-                vv = p.vals[b0 + lane];
-                if (kv != p.sentinel && !(vv & OCC_DENSE)) cv = coefl[vv & OCC_PAYLOAD];
-            }
-            for (int i = 0; i < cnt; ++i) {
-                const unsigned ki = __shfl_sync(FULL, kv, i);
-                if (ki == p.sentinel) break;               // warp-uniform; the sentinels sort to the end
-                if (ki != run_key) {
-                    // the finished run lies inside the chunk unless it began at the chunk start AND continues the previous chunk
-                    if (run_from_start && run_key == prev_last) store_row<VPL>(acc, carry, 0, d4, lane);
-                    else {
+    float gs[NL];
 #pragma unroll
-                        for (int q = 0; q < VPL; ++q) acc.v[q] = gs * acc.v[q];
-                        store_row<VPL>(acc, p.out[l], run_key, d4, lane);
-                    }
-                    acc.zero();
-                    run_key = ki;
-                    run_from_start = false;
-                }
-                const unsigned vi = __shfl_sync(FULL, vv, i);
-                if (vi & OCC_DENSE) {
+    for (int l = 0; l < NL; ++l) gs[l] = p.gloss[l] * p.inv_pairs;
+    float* carry = p.carry + (size_t)c * 2 * NL * row_f;
+    Row<VPL> acc[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) acc[l].zero();
+    unsigned run_key = first_key;
+    bool run_from_start = true;                            // the current run began at the first occurrence of the chunk
+
+    auto finish_run = [&](bool to_head_slot, bool to_tail_slot) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (to_head_slot) store_row<VPL>(acc[l], carry, l, d4, lane);
+            else if (to_tail_slot) store_row<VPL>(acc[l], carry, NL + l, d4, lane);
+            else {
+#pragma unroll
+                for (int q = 0; q < VPL; ++q) acc[l].v[q] = gs[l] * acc[l].v[q];
+                store_row<VPL>(acc[l], p.out[l], run_key, d4, lane);
+            }
+            acc[l].zero();
+        }
+    };
+
+    for (int64_t b0 = base; b0 < end; b0 += 32) {
+        const int cnt = (int)min((int64_t)32, end - b0);
+        unsigned kv = p.sentinel, vv = 0u, rec = 0u;
+        float cv[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) cv[l] = 0.f;
+        if (lane < cnt) {
+            kv = p.keys[b0 + lane];
+            vv = p.vals[b0 + lane];
+            if (kv != p.sentinel && !(vv & OCC_DENSE)) {
+                const unsigned m = vv & OCC_PAYLOAD;
+                rec = (unsigned)((m % (unsigned)p.B) * (unsigned)p.K1 + m / (unsigned)p.B);     // record index [b][k]
+#pragma unroll
+                for (int l = 0; l < NL; ++l) cv[l] = p.coef[(size_t)l * p.M + rec];
+            } else {
+                rec = vv & OCC_PAYLOAD;                                                            // dense record: positive b
+            }
+        }
+        bool any = (vv & OCC_DENSE) != 0u;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) any |= cv[l] != 0.f;
+        const unsigned live = __ballot_sync(FULL, any && kv != p.sentinel);
+        const unsigned valid = __ballot_sync(FULL, kv != p.sentinel);
+        const int n_valid = __popc(valid);                 // the sentinels sort to the end: valid lanes are a prefix
+        for (int i = 0; i < n_valid; ++i) {
+            const unsigned ki = __shfl_sync(FULL, kv, i);
+            if (ki != run_key) {
+                // the finished run lies inside the chunk unless it began at the chunk start AND continues the previous chunk
+                finish_run(run_from_start && run_key == prev_last, false);
+                run_key = ki;
+                run_from_start = false;
+            }
+            if (!((live >> i) & 1u)) continue;             // inactive negative in every layer: nothing to add (warp-uniform)
+            const unsigned vi = __shfl_sync(FULL, vv, i);
+            const unsigned ri = __shfl_sync(FULL, rec, i);
+            if (vi & OCC_DENSE) {
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
                     Row<VPL> dr;
-                    load_row<VPL, true>(dr, dhrl, vi & OCC_PAYLOAD, d4, lane);
+                    load_row<VPL, true>(dr, p.dhr + (size_t)l * p.B * row_f, ri, d4, lane);
 #pragma unroll
-                    for (int q = 0; q < VPL; ++q) acc.v[q] = acc.v[q] + dr.v[q];
-                } else {
-                    const float ci = __shfl_sync(FULL, cv, i);
-                    if (ci != 0.f) {                       // inactive negatives cost nothing (warp-uniform)
-                        const unsigned bits = (unsigned)maskl[(size_t)(vi & OCC_PAYLOAD) * 32 + lane];
-                        add_signed<VPL>(acc, (vi & OCC_HR) ? ci : -ci, bits);
-                    }
+                    for (int q = 0; q < VPL; ++q) acc[l].v[q] = acc[l].v[q] + dr.v[q];
+                }
+            } else {
+                unsigned bits[NL];
+#pragma unroll
+                for (int l = 0; l < NL; ++l)
+                    bits[l] = (unsigned)reinterpret_cast<const smask_t*>(p.smask)[((size_t)l * p.M + ri) * 32 + lane];
+                const float sgn = (vi & OCC_HR) ? 1.f : -1.f;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const float ci = __shfl_sync(FULL, cv[l], i);
+                    if (ci != 0.f) add_signed<VPL>(acc[l], sgn * ci, bits[l]);
                 }
             }
         }
-        // the last run of the chunk
-        const bool head = run_from_start && run_key == prev_last;
-        const bool tail = run_key == next_first;
-        if (head) store_row<VPL>(acc, carry, 0, d4, lane);             // (head && tail: the whole chunk is one through-run, slot 0)
-        else if (tail) store_row<VPL>(acc, carry, 1, d4, lane);
-        else {
-#pragma unroll
-            for (int q = 0; q < VPL; ++q) acc.v[q] = gs * acc.v[q];
-            store_row<VPL>(acc, p.out[l], run_key, d4, lane);
-        }
+        if (n_valid < cnt) break;                          // the rest of the chunk is sentinels
     }
+    // the last run of the chunk
+    const bool head = run_from_start && run_key == prev_last;
+    const bool tail = run_key == next_first;
+    finish_run(head, !head && tail);                       // (head && tail: the whole chunk is one through-run, slot 0)
 }
 
 // Pass B: the chunk in which a multi-chunk run STARTS finishes it: its own tail partial plus the head partials of the following
 // chunks, in list order, while they continue the same key.
 template <int VPL>
-__global__ void __launch_bounds__(256) transe_fixup_kernel(ReduceParams p) {
+__global__ void __launch_bounds__(256) transe_fixup_kernel(ReduceParams p, int NL) {
     const int lane = threadIdx.x & 31;
     const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (c >= p.n_chunks) return;
@@ -367,16 +423,15 @@ __global__ void __launch_bounds__(256) transe_fixup_kernel(ReduceParams p) {
     if (p.keys[base] == key && c > 0 && p.keys[base - 1] == key) return;
     const int d4 = p.d4;
     const size_t row_f = (size_t)d4 * 4;
-    for (int l = 0; l < p.n_layers; ++l) {
+    for (int l = 0; l < NL; ++l) {
         const float gs = p.gloss[l] * p.inv_pairs;
-        const float* carry_l = p.carry + (size_t)l * p.n_chunks * 2 * row_f;
         Row<VPL> acc;
-        load_row<VPL, true>(acc, carry_l + (size_t)c * 2 * row_f, 1, d4, lane);
+        load_row<VPL, true>(acc, p.carry + ((size_t)c * 2 + 1) * NL * row_f, l, d4, lane);
         for (int64_t c2 = c + 1; c2 < p.n_chunks; ++c2) {
             const int64_t b2 = c2 * p.chunk, e2 = min(p.n_occ, b2 + p.chunk);
             if (p.keys[b2] != key) break;
             Row<VPL> part;
-            load_row<VPL, true>(part, carry_l + (size_t)c2 * 2 * row_f, 0, d4, lane);
+            load_row<VPL, true>(part, p.carry + (size_t)c2 * 2 * NL * row_f, l, d4, lane);
 #pragma unroll
             for (int q = 0; q < VPL; ++q) acc.v[q] = acc.v[q] + part.v[q];
             const bool through = p.keys[e2 - 1] == key && e2 < p.n_occ && p.keys[e2] == key;
@@ -388,6 +443,8 @@ __global__ void __launch_bounds__(256) transe_fixup_kernel(ReduceParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pair cosine (alignment losses).  Its backward scatters with vector REDs: a few thousand seed links, collisions are rare.
 template <int VPL>
 __device__ __forceinline__ void red_row(float* base, int64_t row, int d4, int lane, const Row<VPL>& v) {
 #pragma unroll
@@ -397,7 +454,6 @@ __device__ __forceinline__ void red_row(float* base, int64_t row, int d4, int la
     }
 }
 
-// ------------------------------------------------------------------------------------------------
 template <int VPL>
 __global__ void __launch_bounds__(256) pair_cos_fwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int d4,
                                                            const int64_t* __restrict__ ia, const int64_t* __restrict__ ib, int64_t M,
@@ -565,10 +621,13 @@ extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* cons
         JMAC_CUDA(cudaMallocAsync(&part_tmp, sizeof(float) * (size_t)n_layers * (size_t)blocks, st));
         p.loss_part = part_tmp;
     }
+    static const int variant = getenv("JMAC_SCORER_VARIANT") ? atoi(getenv("JMAC_SCORER_VARIANT")) : 0;
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL <= 2 ? 4 : 2;
-        if (record) transe_fwd_kernel<VPL, U, true><<<(unsigned)blocks, threads, 0, st>>>(p);
-        else transe_fwd_kernel<VPL, U, false><<<(unsigned)blocks, threads, 0, st>>>(p);
+        if (!record) transe_fwd_kernel<VPL, U, false, 3><<<(unsigned)blocks, threads, 0, st>>>(p);
+        else if (variant == 1) transe_fwd_kernel<VPL, U, true, 2><<<(unsigned)blocks, threads, 0, st>>>(p);       // no spills, 16 warps / SM
+        else if (variant == 2) transe_fwd_kernel<VPL, 2, true, 3><<<(unsigned)blocks, threads, 0, st>>>(p);       // 2 rows in flight per warp, 24 warps / SM
+        else transe_fwd_kernel<VPL, U, true, 3><<<(unsigned)blocks, threads, 0, st>>>(p);                         // 24 warps / SM, some spills
     });
     JMAC_LAUNCH_CHECK();
     transe_loss_kernel<<<n_layers, 256, 0, st>>>(p.loss_part, (int)blocks, margin, 1.f / ((float)B * (float)(p.K1 - 1)), loss);
@@ -605,7 +664,7 @@ extern "C" int jmac_transe_margin_bwd(int n_layers, int d, const int64_t* h, con
     cub_bytes = L.cub_bytes;
     JMAC_CUDA(cub::DeviceRadixSort::SortPairs(w + L.off_cub, cub_bytes, rkeys, rkeys2, rvals, rvals2, (int)L.n_rocc, 0, bits_for_u((uint64_t)n_rel), st));
     ReduceParams q;
-    q.n_layers = n_layers; q.d4 = d / 4; q.M = M; q.B = B;
+    q.d4 = d / 4; q.K1 = K1; q.M = M; q.B = B;
     {
         const char* rw = reinterpret_cast<const char*>(record);
         q.coef = reinterpret_cast<const float*>(rw);  rw += align256(4 * (size_t)n_layers * M);
@@ -626,9 +685,14 @@ extern "C" int jmac_transe_margin_bwd(int n_layers, int d, const int64_t* h, con
         q.n_chunks = pass == 0 ? L.e_chunks : L.r_chunks;
         for (int l = 0; l < n_layers; ++l) q.out[l] = pass == 0 ? d_ent[l] : d_rel[l];
         const unsigned blocks = (unsigned)((q.n_chunks * 32 + 255) / 256);
-        JMAC_DISPATCH_VPL(d, { transe_reduce_kernel<VPL><<<blocks, 256, 0, st>>>(q); });
+        JMAC_DISPATCH_VPL(d, {
+            if (n_layers == 1) transe_reduce_kernel<VPL, 1><<<blocks, 256, 0, st>>>(q);
+            else if (n_layers == 2) transe_reduce_kernel<VPL, 2><<<blocks, 256, 0, st>>>(q);
+            else if (n_layers == 3) transe_reduce_kernel<VPL, 3><<<blocks, 256, 0, st>>>(q);
+            else transe_reduce_kernel<VPL, 4><<<blocks, 256, 0, st>>>(q);
+        });
         JMAC_LAUNCH_CHECK();
-        JMAC_DISPATCH_VPL(d, { transe_fixup_kernel<VPL><<<blocks, 256, 0, st>>>(q); });
+        JMAC_DISPATCH_VPL(d, { transe_fixup_kernel<VPL><<<blocks, 256, 0, st>>>(q, n_layers); });
         JMAC_LAUNCH_CHECK();
     }
     return 0;

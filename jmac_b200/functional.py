@@ -448,6 +448,80 @@ def node_mm(X: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     return torch.mm(X, W)
 
 
+class ConcatLinearFn(torch.autograd.Function):
+    """``torch.mm(torch.cat(xs, 1), W)`` without the concatenation: sum_i xs[i] @ W[rows of block i], every product after the
+    first accumulated in the GEMM epilogue of the next (src/jmac_model.py:185,194,203: the name / alignment channel)."""
+
+    @staticmethod
+    def forward(ctx, W, *xs):
+        xs = [_f32c(x) for x in xs]
+        W = _f32c(W)
+        out, off = None, 0
+        for x in xs:
+            k = x.shape[1]
+            out = gemm_nn(x, W[off:off + k]) if out is None else gemm_nn(x, W[off:off + k], add1=out, out=out)
+            off += k
+        ctx.save_for_backward(W, *xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, G):
+        W, *xs = ctx.saved_tensors
+        G = _f32c(G)
+        dW = torch.empty_like(W) if ctx.needs_input_grad[0] else None
+        dxs, off = [], 0
+        for i, x in enumerate(xs):
+            k = x.shape[1]
+            dxs.append(gemm_nt(G, W[off:off + k]) if ctx.needs_input_grad[1 + i] else None)
+            if dW is not None:
+                dW[off:off + k] = gemm_tn(x, G)
+            off += k
+        return (dW, *dxs)
+
+
+def concat_linear(xs: Sequence[torch.Tensor], W: torch.Tensor) -> torch.Tensor:
+    """``torch.mm(torch.cat(xs, dim=1), W)``; large node tables skip the [N, sum k_i] concatenation."""
+    M, N = xs[0].shape[0], W.shape[1]
+    ok = all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and _tc_eligible(M, x.shape[1], N) and _tn_eligible(M, x.shape[1], N)
+             and _tc_eligible(M, N, x.shape[1]) for x in xs)
+    if ok and sum(x.shape[1] for x in xs) == W.shape[0]:
+        return ConcatLinearFn.apply(W, *xs)
+    return torch.mm(torch.cat(list(xs), dim=1), W)
+
+
+class RowNormalizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        lib = _lib.load()
+        x = _f32c(x)
+        N, d = x.shape
+        y = torch.empty_like(x)
+        need = ctx.needs_input_grad[0]
+        inv = torch.empty(N, dtype=torch.float32, device=x.device) if need else None
+        with torch.cuda.device(x.device):
+            check(lib.jmac_row_normalize_fwd(ptr(x), N, d, float(eps), ptr(y), ptr(inv), stream_ptr()), "jmac_row_normalize_fwd")
+        if need:
+            ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        y, inv = ctx.saved_tensors
+        g = _f32c(g)
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            check(lib.jmac_row_normalize_bwd(ptr(y), ptr(inv), ptr(g), y.shape[0], y.shape[1], ptr(dx), stream_ptr()), "jmac_row_normalize_bwd")
+        return dx, None
+
+
+def row_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """``F.normalize(x, 2, -1)`` for a [N, d] table (one kernel each way); other shapes / dtypes go to the library op."""
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 4 == 0 and 4 <= x.shape[1] <= 512:
+        return RowNormalizeFn.apply(x, eps)
+    return torch.nn.functional.normalize(x, 2, -1, eps)
+
+
 # ----------------------------------------------------------------------------------------------
 # BatchNorm1d(over nodes) + tanh
 # ----------------------------------------------------------------------------------------------

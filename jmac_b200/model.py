@@ -193,23 +193,23 @@ class JMAC(BaseModel):
         dev = self.ent_init_att_completion.device
         e0 = self.ent_init_att_completion[lo:hi]
         name = torch.mm(self._name_table(dev)[lo:hi], self.name_linear)
-        e0n = self.completion_dropout(F.normalize(e0))
-        a0 = torch.mm(torch.cat((e0n, name), dim=1), self.uni_linear1_1)
+        e0n = self.completion_dropout(JF.row_normalize(e0))
+        a0 = JF.concat_linear((e0n, name), self.uni_linear1_1)            # cat(e0n, name) @ W without the concatenation
         a1 = self.conv1_alignment(a0, self.rel_init_att_alignment[rlo:rhi], edge_index, edge_type)
         align_embs = [a0, a1]
         comp_embs = [e0]
         comp_rels = [self.rel_init_att_completion[rlo:rhi]]
         if self.args.num_gcn_layer == 2:
             c1 = self.conv1_completion(e0, self.rel_init_att_completion[rlo:rhi], edge_index, edge_type)
-            c1n = self.completion_dropout(F.normalize(c1))
-            a_in = torch.mm(torch.cat((c1n, a1), dim=1), self.uni_linear2_1)
+            c1n = self.completion_dropout(JF.row_normalize(c1))
+            a_in = JF.concat_linear((c1n, a1), self.uni_linear2_1)
             r1 = torch.mm(self.atv_mlp(torch.mm(self.rel_init_att_completion[rlo:rhi], self.rel_linear11)), self.rel_linear12)
             ar = torch.mm(self.atv_mlp(torch.mm(self.rel_init_att_alignment[rlo:rhi], self.rel_linear11_uni)), self.rel_linear12_uni)
             a2 = self.conv2_alignment(a_in, ar, edge_index, edge_type)
             align_embs.append(a2)
             comp_embs.append(c1)
             comp_rels.append(r1)
-        out = torch.mm(torch.cat(align_embs, dim=1), self.all_linear_completion)
+        out = JF.concat_linear(align_embs, self.all_linear_completion)
         return out, comp_embs, comp_rels
 
     def forward_no_name(self, edge_index, edge_type, ent_bases, rel_bases):
@@ -227,8 +227,8 @@ class JMAC(BaseModel):
     def get_emb(self, edge_index, edge_type, ent_bases, rel_bases, pyt=False):
         """:223-234."""
         a, comps, _ = self.forward_base(edge_index, edge_type, ent_bases, rel_bases)
-        a = F.normalize(a, 2, -1)
-        c = F.normalize(comps[-1], 2, -1)
+        a = JF.row_normalize(a)
+        c = JF.row_normalize(comps[-1])
         if pyt:
             return a.detach().cpu(), c.detach().cpu()
         return a.detach().cpu().numpy(), c.detach().cpu().numpy()
@@ -299,7 +299,7 @@ class JMAC(BaseModel):
         L = self.args.num_gcn_layer
         ents, rels = (ents1, rels1) if source else (ents2, rels2)
         if getattr(self.args, "normalize_triples", False):   # JMAC_DBPv1/models/jmac_model.py:245-247 scores unit-norm h, r, t
-            ents, rels = [F.normalize(e, 2, -1) for e in ents[:L]], [F.normalize(r, 2, -1) for r in rels[:L]]
+            ents, rels = [JF.row_normalize(e) for e in ents[:L]], [JF.row_normalize(r) for r in rels[:L]]
         align = 0
         for layer in range(L):
             align = align + self.alignment_loss_simple(links, ents1[layer], ents2[layer])

@@ -78,3 +78,53 @@ def test_gemm_epilogue_addends_and_in_place_accumulate(M, K, N):
     assert float(((only2.double() - (ref - D1.double())).abs() / bound).max()) < 2e-6
     with pytest.raises(ValueError):
         JF.gemm_nt(A, B, add1=D1[:, : N // 2])
+
+
+@pytest.mark.parametrize("d", [32, 256, 300, 512])
+def test_row_normalize_matches_torch(d):
+    """F.normalize(x, 2, -1) forward and backward in one kernel each, including a zero row (the eps clamp: no norm gradient)."""
+    from jmac_b200 import functional as JF
+    torch.manual_seed(d)
+    x = torch.randn(777, d, device="cuda")
+    x[5] = 0
+    x[6] *= 1e-14                                           # below eps = 1e-12: y = x / eps
+    g = torch.randn(777, d, device="cuda")
+    a = x.clone().requires_grad_(True)
+    b = x.double().clone().requires_grad_(True)
+    ya = JF.row_normalize(a)
+    yb = torch.nn.functional.normalize(b, 2, -1)
+    (ya * g).sum().backward()
+    (yb * g.double()).sum().backward()
+    torch.testing.assert_close(ya.detach().double(), yb.detach(), rtol=1e-6, atol=1e-7)
+    scale = float(b.grad.abs().max())
+    rows = torch.ones(777, dtype=torch.bool, device="cuda")
+    rows[6] = False                                         # the 1e12-scaled row is compared relative to itself
+    assert float((a.grad.double() - b.grad)[rows].abs().max()) <= 1e-5 * float(b.grad[rows].abs().max())
+    assert float((a.grad.double() - b.grad)[6].abs().max()) <= 1e-5 * float(b.grad[6].abs().max())
+    with torch.no_grad():
+        assert torch.equal(JF.row_normalize(x), ya.detach())
+
+
+def test_concat_linear_matches_cat_mm():
+    """cat(xs, 1) @ W as a sum of products accumulated in GEMM epilogues (the name / alignment channel of forward_name)."""
+    from jmac_b200 import functional as JF
+    torch.manual_seed(0)
+    N, d = 6000, 256
+    for widths in ((256, 256), (256, 256, 256), (128, 256)):
+        xs = [torch.randn(N, k, device="cuda", requires_grad=True) for k in widths]
+        W = (torch.randn(sum(widths), d, device="cuda") * 0.1).requires_grad_(True)
+        G = torch.randn(N, d, device="cuda")
+        out = JF.concat_linear(xs, W)
+        out.backward(G)
+        xr = [x.detach().double().requires_grad_(True) for x in xs]
+        Wr = W.detach().double().requires_grad_(True)
+        ref = torch.cat(xr, 1) @ Wr
+        ref.backward(G.double())
+        assert relerr(out.detach(), ref.detach()) < 5e-6
+        assert relerr(W.grad, Wr.grad) < 1e-5
+        for x, r in zip(xs, xr):
+            assert relerr(x.grad, r.grad) < 5e-6
+    # small tables: the library path, same values as the plain expression
+    xs = [torch.randn(100, 64, device="cuda"), torch.randn(100, 300, device="cuda")]
+    W = torch.randn(364, 64, device="cuda")
+    assert torch.equal(JF.concat_linear(xs, W), torch.mm(torch.cat(xs, 1), W))
