@@ -557,7 +557,7 @@ def run_b200(args):
             X = x0.detach()
         agg, lse, Tbuf = torch.empty_like(X), torch.empty(N, device=dev), torch.empty_like(X)
         dP, dXe, dQ = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
-        dRp, dS, da = torch.empty_like(Rp), torch.empty_like(Rp), torch.zeros(d, device=dev)
+        dRp, dS, da, gsum = torch.empty_like(Rp), torch.empty_like(Rp), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
         rec = int(lib.jmac_edge_record_bytes(d))
         erec = torch.empty(E * rec, dtype=torch.uint8, device=dev)
         ptr, st = _lib.ptr, _lib.stream_ptr
@@ -565,7 +565,7 @@ def run_b200(args):
         k_fwd = lambda: _lib.check(lib.jmac_edge_fwd_fused(plan.handle, ptr(P), ptr(Q), ptr(X), ptr(S), ptr(Rp), ptr(a), 0.05, d, ptr(agg),
                                                            ptr(lse), ptr(X), ptr(Tbuf), ptr(erec), st()))
         k_dst = lambda: _lib.check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(X), ptr(Rp), ptr(a), 0.05, d, ptr(agg), ptr(lse), ptr(gout),
-                                                         ptr(dP), ptr(erec), ptr(da), st()))
+                                                         ptr(dP), ptr(erec), ptr(da), ptr(gsum), st()))
         k_src = lambda: _lib.check(lib.jmac_edge_bwd_src(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st()))
         k_rel = lambda: _lib.check(lib.jmac_edge_bwd_rel(plan.handle, ptr(gout), ptr(erec), ptr(a), 0.05, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st()))
         row = d * 4

@@ -110,10 +110,13 @@ size_t jmac_edge_record_bytes(int d);
  * d a = sum_i P[i](.)mu_i + sum_j Q[j](.)nu_j - sum_t S[t](.)omega_t with the per-segment sums of
  * ds_e * LeakyReLU'(z_e) that the passes form anyway.
  * Destination pass: reads the forward's logits and masks from erec, gathers X[j]; writes dP[N_dst,d]
- * and the {alpha*sqrt(deg), ds_e} part of erec. */
+ * and the {alpha*sqrt(deg), ds_e} part of erec.  g_colsum[d] (may be NULL; caller zeroes): ACCUMULATES the column sums of G
+ * over the destinations -- the gradient of the self-loop relation row of the fused forward (T = agg + X - R'[loop]), picked up
+ * while every G row passes through anyway instead of by a separate reduction over the [N,d] table. */
 int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X, const float* Rp,
                       const float* a_att, float leaky_slope, int d, const float* agg, const float* lse,
-                      const float* G, float* dP, void* erec, float* da_att, void* stream);
+                      const float* G, float* dP, void* erec, float* da_att, float* g_colsum,
+                      void* stream);
 /* Source pass (by-source ordering): dXe[N_src,d] = sum over out-edges of alpha*sqrt(deg)*G[i] (the
  * x_j gather's gradient, replaces index_put_(accumulate)); dQ[N_src,d] = a_att (.) nu_j. */
 int jmac_edge_bwd_src(jmac_plan* plan, const float* G, const void* erec, const float* a_att,

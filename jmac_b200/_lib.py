@@ -27,7 +27,7 @@ _SIGNATURES = {
     "jmac_edge_fwd": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P]),
     "jmac_edge_fwd_fused": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
     "jmac_edge_record_bytes": (c_size_t, [c_int]),
-    "jmac_edge_bwd_dst": (c_int, [P, P, P, P, P, c_float, c_int, P, P, P, P, P, P, P]),
+    "jmac_edge_bwd_dst": (c_int, [P, P, P, P, P, c_float, c_int, P, P, P, P, P, P, P, P]),
     "jmac_edge_bwd_src": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "jmac_edge_bwd_rel": (c_int, [P, P, P, P, c_float, c_int, P, P, P, P, P]),
     "jmac_bn_stats": (c_int, [P, c_int64, c_int, P, P]),

@@ -38,6 +38,8 @@ struct EdgeBwdDstParams {
     const void* mask;    // [E][32] lanes x mask_t               in (forward)
     const float* logit;  // [E]                                  in (forward)
     float* da;           // [d] accumulated
+    float* gsum;         // [d] accumulated column sums of G over the destinations (null: not wanted): the gradient of the self-loop
+                         // relation row that the fused forward subtracts from every node (T = agg + X - R'[loop])
     float* partial;      // [n_slots, d]
 };
 
@@ -67,9 +69,10 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int d4 = p.d4;
-    Row<VPL> av, da_acc;
+    Row<VPL> av, da_acc, gs_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     da_acc.zero();
+    gs_acc.zero();
     const mask_t* maskp = reinterpret_cast<const mask_t*>(p.mask);
     const float hi = 1.f - p.slope;
 
@@ -77,6 +80,10 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
         const Item item = p.items[it];
         Row<VPL> gi, mu;          // mu: sum over edges with z > 0 of ds_e, per feature
         load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
+        if (p.gsum && (it == 0 || p.items[it - 1].seg != item.seg)) {       // every destination once (the first item of its segment)
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) gs_acc.v[i] = gs_acc.v[i] + gi.v[i];
+        }
         mu.zero();
         float gdot = 0.f, ds_sum = 0.f;
         {
@@ -160,6 +167,10 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
         else store_row<VPL>(mu, p.partial, item.slot, d4, lane);
     }
     flush_da<VPL>(da_acc, p.da, d4);
+    if (p.gsum) {
+        __syncthreads();
+        flush_da<VPL>(gs_acc, p.gsum, d4);
+    }
 }
 
 // Sum of the partial rows of split segments: out[seg] = sum_k partial[first + k]; `rows` rows per slot.
@@ -408,9 +419,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
     constexpr int BWD_RING_S = BwdRing<VPL>::S;
     Ring<BWD_RING_S> ring;
     ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
-    Row<VPL> av, da_acc;
+    Row<VPL> av, da_acc, gs_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     da_acc.zero();
+    gs_acc.zero();
     const float hi = 1.f - p.slope;
     constexpr int ADV = (32 - BWD_RING_S) & ~1;
 
@@ -437,6 +449,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
             }
             Row<VPL> gi, mu;
             load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
+            if (p.gsum && (it == 0 || __ldg(&p.items[it - 1].seg) != item.seg)) {   // every destination once (first item of its segment)
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) gs_acc.v[i] = gs_acc.v[i] + gi.v[i];
+            }
             mu.zero();
             float gdot = 0.f, ds_sum = 0.f;
             {
@@ -533,6 +549,10 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
         if (batch_base + lane < stream_end) p.ew[batch_base + lane] = make_float2(w_keep, ds_keep);
     }
     flush_da16<VPL>(da_acc, p.da, d4);
+    if (p.gsum) {
+        __syncthreads();
+        flush_da16<VPL>(gs_acc, p.gsum, d4);
+    }
 }
 
 template <int VPL, int MODE, bool FULLROW>
@@ -663,7 +683,7 @@ extern "C" size_t jmac_edge_record_bytes(int d) { return dim_ok(d) ? 8 + edge_ma
 
 extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X, const float* Rp, const float* a_att, float leaky_slope,
                                  int d, const float* agg, const float* lse, const float* G, float* dP, void* erec, float* da_att,
-                                 void* stream) {
+                                 float* g_colsum, void* stream) {
     JMAC_ARG(plan && P && X && Rp && a_att && agg && lse && G && dP && da_att);
     JMAC_ARG(plan->E == 0 || erec != nullptr);
     JMAC_ARG((reinterpret_cast<uintptr_t>(erec) & 31) == 0);
@@ -679,6 +699,7 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
     p.mask = erec_mask(erec, plan->E);
     p.logit = erec_logit(erec, plan->E, d);
     p.da = da_att;
+    p.gsum = g_colsum;
     p.partial = nullptr;
     if (plan->dst_items.n_slots > 0) {
         int rc = plan_scratch(plan, sizeof(float) * (size_t)plan->dst_items.n_slots * (size_t)d, &p.partial, st);

@@ -283,11 +283,12 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
         Wt, Wb = W_att[:d], W_att[d:]
         dP, dXe, dQ = torch.empty_like(x_loc), torch.empty_like(Xf), torch.empty_like(Xf)
         dRp, dS = torch.empty_like(Rp), torch.empty_like(S)
-        da = torch.zeros(d, dtype=torch.float32, device=dev)
+        acc2 = torch.zeros(2, d, dtype=torch.float32, device=dev)     # [0] = d a_att, [1] = column sums of G over this shard
+        da, gsum = acc2[0], acc2[1]
         with torch.cuda.device(dev):
             st = stream_ptr()
             check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Xf), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
-                                        ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
+                                        ptr(erec), ptr(da), ptr(gsum), st), "jmac_edge_bwd_dst")
             check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
                   "jmac_edge_bwd_src")
         # the partial input gradient of every gathered row, chunk by chunk, each chunk handed to NCCL as soon as it exists
@@ -302,7 +303,7 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), stream_ptr()),
                   "jmac_edge_bwd_rel")
-        dRp[-1] -= G.sum(0)                                   # T = agg + x_loc - Rp[-1]
+        dRp[-1] -= gsum                                       # T = agg + x_loc - Rp[-1]
         JF.small_mm_nt_acc(dS, Wb, dRp)                       # S = Rp Wb: dRp += dS Wb^T
         dXd = JF.gemm_nt(dP, Wt, add1=G)                      # dP W_top^T + dT
         dW = None

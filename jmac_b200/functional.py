@@ -207,11 +207,12 @@ class EdgePhaseFn(torch.autograd.Function):
         dQ = torch.empty_like(X)
         dRp = torch.empty_like(Rp)
         dS = torch.empty_like(S)
-        da = torch.zeros(d, dtype=torch.float32, device=dev)
+        acc = torch.zeros(2, d, dtype=torch.float32, device=dev)      # [0] = d a_att, [1] = column sums of G (fused self loop)
+        da, gsum = acc[0], (acc[1] if ctx.fused else None)
         with torch.cuda.device(dev):
             st = stream_ptr()
             check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(X), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
-                                        ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
+                                        ptr(erec), ptr(da), ptr(gsum), st), "jmac_edge_bwd_dst")
             check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
                   "jmac_edge_bwd_src")
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st),
@@ -219,7 +220,7 @@ class EdgePhaseFn(torch.autograd.Function):
         dXself = None
         if ctx.fused:
             dXself = G                                  # T = agg + Xself - Rp[-1]
-            dRp[-1] -= G.sum(0)
+            dRp[-1] -= gsum
         return None, dP, dQ, dXe, dS, dRp, da.view(ctx.a_shape), None, dXself
 
 
@@ -273,16 +274,17 @@ class AttnEdgeFn(torch.autograd.Function):
         Wt, Wb = W_att[:d], W_att[d:]
         dP, dXe, dQ = torch.empty_like(Xd), torch.empty_like(Xs), torch.empty_like(Xs)
         dRp, dS = torch.empty_like(Rp), torch.empty_like(S)
-        da = torch.zeros(d, dtype=torch.float32, device=dev)
+        acc = torch.zeros(2, d, dtype=torch.float32, device=dev)      # [0] = d a_att, [1] = column sums of G
+        da, gsum = acc[0], acc[1]
         with torch.cuda.device(dev):
             st = stream_ptr()
             check(lib.jmac_edge_bwd_dst(plan.handle, ptr(P), ptr(Xs), ptr(Rp), ptr(a), slope, d, ptr(agg), ptr(lse), ptr(G), ptr(dP),
-                                        ptr(erec), ptr(da), st), "jmac_edge_bwd_dst")
+                                        ptr(erec), ptr(da), ptr(gsum), st), "jmac_edge_bwd_dst")
             check(lib.jmac_edge_bwd_src(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(Q), ptr(dXe), ptr(dQ), ptr(da), st),
                   "jmac_edge_bwd_src")
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), st),
                   "jmac_edge_bwd_rel")
-        dRp[-1] -= G.sum(0)                                   # T = agg + Xd - Rp[-1]
+        dRp[-1] -= gsum                                       # T = agg + Xd - Rp[-1]: column sums of G, picked up by the destination pass
         small_mm_nt_acc(dS, Wb, dRp)                          # S = Rp Wb: dRp += dS Wb^T
         dXd = dXs = dW = None
         if same:
