@@ -40,6 +40,10 @@ uint64_t jmac_launch_count(void);
  * bit 3: negative sampler: (h, r) out of range or fewer than k valid entities);
  * synchronise the stream first to be sure the kernels in question have run. */
 int jmac_status_poll(void);
+/* Withhold n_sms SMs from the persistent (one CTA per SM) kernels of this library, process-wide; returns the previous value.
+ * For callers that overlap a communication kernel (NCCL) with them: a persistent CTA fills its SM's shared memory, so a
+ * collective launched meanwhile could otherwise only start in the gaps between kernels. */
+int jmac_set_sm_reserve(int n_sms);
 
 /* ------------------------------------------------------------------------------------------
  * Graph plan: CSR-by-destination (+ by-source and by-relation orderings used by backward).

@@ -19,6 +19,7 @@ _SIGNATURES = {
     "jmac_last_error": (c_char_p, []),
     "jmac_launch_count": (ctypes.c_uint64, []),
     "jmac_status_poll": (c_int, []),
+    "jmac_set_sm_reserve": (c_int, [c_int]),
     "jmac_plan_create": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_create_bipartite": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_destroy": (c_int, [P]),

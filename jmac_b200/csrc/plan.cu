@@ -40,11 +40,15 @@ int* status_words() {
     return host;      // unified addressing: the same pointer is valid on every device
 }
 
+// SMs the persistent kernels may occupy.  jmac_set_sm_reserve(r) withholds r SMs: a communication kernel running next to a
+// persistent one-CTA-per-SM compute kernel (which fills every SM's shared memory) can then always be scheduled (jmac_b200.dist).
+static int g_sm_reserve = 0;
 int sm_count() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    return n;
+    const int r = __atomic_load_n(&g_sm_reserve, __ATOMIC_RELAXED);
+    return n - r > 8 ? n - r : n;
 }
 
 // Stream-ordered allocation for the plan and its build temporaries: cudaMalloc / cudaFree serialise the device and
@@ -278,6 +282,11 @@ using namespace jmac;
 extern "C" const char* jmac_version(void) { return "jmac_b200 0.1 (sm_100a)"; }
 extern "C" const char* jmac_last_error(void) { return jmac::g_err; }
 extern "C" uint64_t jmac_launch_count(void) { return __atomic_load_n(&jmac::g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int jmac_set_sm_reserve(int n_sms) {
+    const int old = __atomic_exchange_n(&jmac::g_sm_reserve, n_sms > 0 ? n_sms : 0, __ATOMIC_RELAXED);
+    return old;
+}
 
 extern "C" int jmac_status_poll(void) {
     int* w = jmac::status_words();
