@@ -145,6 +145,12 @@ def _backend(group) -> str:
     return dist.get_backend(group)
 
 
+import os as _os
+# diagnostics (profiles/multi_gpu_overlap_r02.md): "nocomm" skips the exchanges (pure per-rank compute time, results meaningless),
+# "serial" waits for every collective right after issuing it (no overlap)
+_DIAG = _os.environ.get("JMAC_DIST_DIAG", "")
+
+
 def _pad_rows(x_loc: torch.Tensor, n_max: int) -> torch.Tensor:
     if x_loc.shape[0] < n_max:
         x_loc = torch.cat([x_loc, x_loc.new_zeros(n_max - x_loc.shape[0], x_loc.shape[1])])
@@ -162,8 +168,14 @@ def gather_rows(x_loc: torch.Tensor, shard: Shard, group, async_op: bool = False
     for c in range(shard.chunks):
         r0, r1 = shard.chunk_rows(c)
         src = buf[c * shard.n_c:(c + 1) * shard.n_c]
-        if _backend(group) == "nccl":
-            works.append(dist.all_gather_into_tensor(out[r0:r1], src, group=group, async_op=async_op))
+        if _DIAG == "nocomm":
+            works.append(None)
+        elif _backend(group) == "nccl":
+            w = dist.all_gather_into_tensor(out[r0:r1], src, group=group, async_op=async_op)
+            if _DIAG == "serial" and w is not None:
+                w.wait()
+                w = None
+            works.append(w)
         else:
             dist.all_gather(list(out[r0:r1].view(shard.world, shard.n_c, d).unbind(0)), src.contiguous(), group=group)
             works.append(None)
@@ -172,8 +184,14 @@ def gather_rows(x_loc: torch.Tensor, shard: Shard, group, async_op: bool = False
 
 def scatter_sum_chunk(g_chunk: torch.Tensor, out_chunk: torch.Tensor, shard: Shard, group, async_op: bool = False):
     """Sum over ranks of one chunk [world * n_c, d] of partial rows; this rank keeps its n_c rows (``out_chunk``)."""
+    if _DIAG == "nocomm":
+        return None
     if _backend(group) == "nccl":
-        return dist.reduce_scatter_tensor(out_chunk, g_chunk, group=group, async_op=async_op)
+        w = dist.reduce_scatter_tensor(out_chunk, g_chunk, group=group, async_op=async_op)
+        if _DIAG == "serial" and w is not None:
+            w.wait()
+            w = None
+        return w
     tmp = g_chunk.clone()                      # gloo has no reduce-scatter
     dist.all_reduce(tmp, group=group)
     out_chunk.copy_(tmp.view(shard.world, shard.n_c, -1)[shard.rank])
