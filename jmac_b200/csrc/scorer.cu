@@ -637,13 +637,11 @@ extern "C" int jmac_transe_margin_fwd(const float* const* ent, const float* cons
         JMAC_CUDA(cudaMallocAsync(&part_tmp, sizeof(float) * (size_t)n_layers * (size_t)blocks, st));
         p.loss_part = part_tmp;
     }
-    static const int variant = getenv("JMAC_SCORER_VARIANT") ? atoi(getenv("JMAC_SCORER_VARIANT")) : 0;
     JMAC_DISPATCH_VPL(d, {
         constexpr int U = VPL <= 2 ? 4 : 2;
         // recording variant: 2 rows per warp in registers, 24 warps / SM (measured against 4 rows with 16 warps or with spills: 2.11 vs
-        // 2.52 / 2.36 ms at B = 65536, K = 64) -- the L2 prefetch above supplies the memory-level parallelism
+        // 2.52 / 2.36 ms at B = 65536, K = 64; 1.77 ms with the L2 prefetch, which supplies the memory-level parallelism)
         if (!record) transe_fwd_kernel<VPL, U, false, 3><<<(unsigned)blocks, threads, 0, st>>>(p);
-        else if (variant == 1) transe_fwd_kernel<VPL, U, true, 2><<<(unsigned)blocks, threads, 0, st>>>(p);
         else transe_fwd_kernel<VPL, 2, true, 3><<<(unsigned)blocks, threads, 0, st>>>(p);
     });
     JMAC_LAUNCH_CHECK();
