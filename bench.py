@@ -299,7 +299,7 @@ def section_c3(dev, rank, lib):
     gen = torch.Generator(device=dev).manual_seed(3)
     out = {"workload": "planted-match unit-norm embeddings, d=256; evaluation.test(metric='cosine', csls_k=10, accurate=True) rows/s = n / time"}
     for n in (2_617, 10_500):
-        e1, e2 = planted_pair(n, D, 1.5, gen, dev)
+        e1, e2 = planted_pair(n, D, 4.0, gen, dev)          # cos(gold) ~ 0.24, next to the largest random similarity: Hits@1 well below 100 %
         h1, h2 = e1.cpu().numpy(), e2.cpu().numpy()
         res = {}
 
