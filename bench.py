@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
 
 Headline workload (BASELINE.json configs[3], "C4"): synthetic KG with 2M entities, 2k relations,
-40M triples (uniform endpoints: no cache reuse, the honest HBM-bound case), d=256, two stacked
+40M triples (Zipf(1.1) in-degree capped at 1e5, uniform sources -- SURVEY 8d's primary variant; --graph uniform is the
+no-reuse variant), d=256, two stacked
 relation-aware GNN layers forward+backward.  One step = one pass of both layers over the whole
 graph; value = layer-edges per second = (2 * E) / step time, whole job.  With N > 1 the SAME graph
 is destination-sharded over the ranks (strong scaling; halo all-gather / reduce-scatter over NCCL).
@@ -422,16 +423,26 @@ def workload_config(n_gpus, scale=1.0):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own algorithm (un-factored per-edge formulation, oracle port) on the host cores of the box,
+    all threads, pinned (OMP_PROC_BIND), one bounded sample of the headline workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(args.steps, 1), max(min(args.warmup, 1), 0)
+    n_thr = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(n_thr)               # torchrun exports OMP_NUM_THREADS=1; set before torch initialises OpenMP
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    steps, warmup = max(min(args.steps, 30), 1), max(min(args.warmup, 10), 0)
     s = CPU_SAMPLE
     eps, dt, threads = cpu_layer_step(s["N"], s["R"], s["E"], steps, warmup)
-    sample = f"one RelationAwareLayer fwd+bwd on N={s['N']}, E={s['E']}, R={s['R']}, d={D} (uniform, mean degree 20 as C4); per-edge throughput"
+    sample = (f"one RelationAwareLayer fwd+bwd per step on a bounded sample of C4: N={s['N']}, E={s['E']}, R={s['R']}, d={D} "
+              f"(uniform, mean degree 20 and width as C4); per-edge throughput, {dt:.2f} s/step")
+    cfg = workload_config(args.gpus)
+    cfg["workload"] = "C4 (bounded CPU sample, the reference materialises [E,2d] and cannot run 40M edges): " + sample
+    cfg.update(entities=s["N"], relations=s["R"], edges=s["E"], layers=1, parallelism="host cores")
     line = {"impl": "reference", "metric": "gnn_layer_edges_per_s_fwd_bwd", "value": eps, "unit": "edges/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args.gpus),
+            "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -596,7 +607,8 @@ def run_b200(args):
         edge_ms = sum(v["ms"] for v in kernels.values())
         edge_bytes = sum(v["algo_bytes"] for v in kernels.values())
         line["roofline"] = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                            "frac": kernels[top]["frac"], "traffic": TRAFFIC_NCU.get(top), "peak_source": peak_src,
+                            "frac": kernels[top]["frac"], "traffic": TRAFFIC_NCU[args.graph].get(top),
+                            "traffic_source": TRAFFIC_NCU[args.graph]["source"] + " (ncu --set full, one launch)", "peak_source": peak_src,
                             "edge_phase_fwd_bwd": {"ms": edge_ms, "GBps": edge_bytes / edge_ms / 1e6, "frac": edge_bytes / edge_ms / 1e6 / hbm_peak,
                                                    "edges_per_s": E / (edge_ms * 1e-3)},
                             "random_row_gather_GBps": gather_gbps,
@@ -907,9 +919,12 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# of this same workload (profiles/ncu_edge_kernels_r01.md); bytes.
-TRAFFIC_NCU = {"edge_fwd": 91.33e9, "edge_bwd_dst": 52.46e9, "edge_bwd_src": 56.69e9, "edge_bwd_rel": 49.99e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this same workload
+# (bytes): Zipf graph -- profiles/ncu_edge_kernels_r02.md; uniform graph -- profiles/ncu_edge_kernels_r01.md
+TRAFFIC_NCU = {"zipf": {"edge_fwd": 91.21e9, "edge_bwd_dst": 50.84e9, "edge_bwd_src": 38.39e9, "edge_bwd_rel": 27.83e9,
+                        "source": "profiles/ncu_edge_kernels_r02.md"},
+               "uniform": {"edge_fwd": 91.33e9, "edge_bwd_dst": 52.46e9, "edge_bwd_src": 56.69e9, "edge_bwd_rel": 49.99e9,
+                           "source": "profiles/ncu_edge_kernels_r01.md"}}
 
 
 def main():

@@ -30,7 +30,7 @@ def main():
             kern = m.group(1)
             hist[kern] = collections.Counter()
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m and kern:
             op = m.group(1)
             hist[kern]["_total"] += 1
