@@ -394,6 +394,8 @@ def default_chunks(group, n_rows_per_rank: int) -> int:
     """Exchange chunks per layer: 4 on NCCL when every chunk still feeds the tensor-core GEMMs (>= 4096 rows), else 1."""
     if _backend(group) != "nccl":
         return 1
+    if _os.environ.get("JMAC_DIST_CHUNKS"):
+        return max(1, int(_os.environ["JMAC_DIST_CHUNKS"]))
     world = dist.get_world_size(group)
     for c in (4, 2):
         if n_rows_per_rank // c * world >= 8192:
