@@ -46,6 +46,20 @@ int jmac_status_poll(void);
 int jmac_set_sm_reserve(int n_sms);
 
 /* ------------------------------------------------------------------------------------------
+ * Peer memory for the multi-GPU exchange (one process per GPU on one node; no counterpart in the single-device reference).
+ * jmac_peer_alloc: a cudaMalloc allocation other processes can map; jmac_ipc_get_handle / jmac_ipc_open / jmac_ipc_close: its
+ * 64-byte CUDA IPC handle, the mapping in a peer process, and its release; jmac_memcpy_async: a device-to-device copy on `stream`
+ * (local or peer-mapped pointers) executed by the copy engines -- no SM is involved, so the transfer really overlaps the
+ * persistent compute kernels.  Ordering across processes is the caller's job (jmac_b200/peer.py uses tiny NCCL all-reduces).
+ * ------------------------------------------------------------------------------------------ */
+int jmac_peer_alloc(size_t bytes, void** out);
+int jmac_peer_free(void* ptr);
+int jmac_ipc_get_handle(void* ptr, unsigned char* handle64);
+int jmac_ipc_open(const unsigned char* handle64, void** out);
+int jmac_ipc_close(void* ptr);
+int jmac_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Graph plan: CSR-by-destination (+ by-source and by-relation orderings used by backward).
  * Replaces the per-call index work of RelationAwareLayer.compute_norm (src/jmac_model.py:99-109)
  * and the gathers of MessagePassing.propagate (modules/helper/message_passing.py:69-81).  Built

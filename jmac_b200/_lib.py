@@ -20,6 +20,12 @@ _SIGNATURES = {
     "jmac_launch_count": (ctypes.c_uint64, []),
     "jmac_status_poll": (c_int, []),
     "jmac_set_sm_reserve": (c_int, [c_int]),
+    "jmac_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "jmac_peer_free": (c_int, [P]),
+    "jmac_ipc_get_handle": (c_int, [P, ctypes.c_char_p]),
+    "jmac_ipc_open": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
+    "jmac_ipc_close": (c_int, [P]),
+    "jmac_memcpy_async": (c_int, [P, P, c_size_t, P]),
     "jmac_plan_create": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_create_bipartite": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_destroy": (c_int, [P]),
