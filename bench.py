@@ -38,6 +38,10 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # one hardware work queue per stream: the peer-memory exchange parks cuStreamWaitValue32 waits on its copy streams, which must
+    # never share a queue with the compute stream (jmac_b200/peer.py); has to be set before the CUDA context exists
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 
 D = 256
@@ -399,6 +403,8 @@ def multi_gpu_parity(dev, world, group):
     out = enc.step(x, rg, gout)
     sh = enc.shard
     lo, hi = sh.lo, sh.hi
+    exchange = "peer memory (copy engines)" if sh.peer is not None else "NCCL"
+    enc.close()
     vals = [rerr(out, h64[lo:hi]), rerr(hs.detach()[lo:hi], h64[lo:hi]), rerr(enc._x_loc.grad, dx64[lo:hi]), rerr(xs.grad[lo:hi], dx64[lo:hi]),
             rerr(rg.grad, dr64), rerr(rs.grad, dr64), rerr(layers[0].w_att.grad, dw64), rerr(single[0].w_att.grad, dw64),
             rerr(out, hs.detach()[lo:hi]), rerr(enc._x_loc.grad, xs.grad[lo:hi])]
@@ -406,7 +412,7 @@ def multi_gpu_parity(dev, world, group):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     v = [float(a) for a in t.tolist()]
     ok = v[0] <= 1e-4 + 2 * v[1] and v[2] <= max(1e-4, 4 * v[3]) * 2 and v[4] <= max(1e-4, 4 * v[5]) * 2 and v[6] <= max(1e-4, 4 * v[7]) * 2
-    return {"graph": f"N={N}, E={E}, R={R}, d={D}, Zipf(1.1) in-degree, 2 layers fwd+bwd", "chunks_per_exchange": sh.chunks,
+    return {"graph": f"N={N}, E={E}, R={R}, d={D}, Zipf(1.1) in-degree, 2 layers fwd+bwd", "chunks_per_exchange": sh.chunks, "exchange": exchange,
             "fused_overlapped_path": bool(JD._fused_eligible(enc.ops, enc._x_loc, sh, D)),
             "vs_float64_oracle": {"out": {"sharded": v[0], "single_gpu": v[1]}, "dX": {"sharded": v[2], "single_gpu": v[3]},
                                   "dR": {"sharded": v[4], "single_gpu": v[5]}, "dW_att": {"sharded": v[6], "single_gpu": v[7]}},
@@ -556,7 +562,9 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic", "config": cfg, "gpu_launches": launches, "clocks": clk.summary()}
     if parity is not None:
         line["multi_gpu_parity"] = parity
-        cfg["exchange"] = f"{runner.shard.chunks} chunks per all-gather / reduce-scatter, overlapped with the chunk GEMMs (jmac_b200.dist.ShardedAttnEdgeFn)"
+        how = ("copy-engine pulls over NVLink peer memory + local sum (jmac_b200.peer), stream-memory-op handshakes" if runner.shard.peer is not None
+               else "NCCL all-gather / reduce-scatter")
+        cfg["exchange"] = f"{runner.shard.chunks} chunks per exchange, {how}, overlapped with the chunk GEMMs (jmac_b200.dist.ShardedAttnEdgeFn)"
     single = world == 1
 
     if single and "roofline" in sections:

@@ -58,6 +58,13 @@ int jmac_ipc_get_handle(void* ptr, unsigned char* handle64);
 int jmac_ipc_open(const unsigned char* handle64, void** out);
 int jmac_ipc_close(void* ptr);
 int jmac_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
+/* Cross-process ordering without an SM (stream memory operations): jmac_stream_write_u32 stores `value` at a LOCAL device word in
+ * stream order; jmac_stream_wait_geq_u32 blocks `stream` until (int32)(*addr - value) >= 0 for a LOCAL device word (peers set it
+ * with a 4-byte jmac_memcpy_async).  jmac_peer_sum: the local half of the peer reduce-scatter, dst[i] (+)= sum over g <
+ * n_slices of src[g * slice_stride + i], i < n, slices added in ascending order (bit-reproducible). */
+int jmac_stream_write_u32(void* addr, unsigned int value, void* stream);
+int jmac_stream_wait_geq_u32(void* addr, unsigned int value, void* stream);
+int jmac_peer_sum(float* dst, const float* src, int n_slices, int64_t slice_stride, int64_t n, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Graph plan: CSR-by-destination (+ by-source and by-relation orderings used by backward).

@@ -26,6 +26,9 @@ _SIGNATURES = {
     "jmac_ipc_open": (c_int, [ctypes.c_char_p, POINTER(c_void_p)]),
     "jmac_ipc_close": (c_int, [P]),
     "jmac_memcpy_async": (c_int, [P, P, c_size_t, P]),
+    "jmac_stream_write_u32": (c_int, [P, ctypes.c_uint32, P]),
+    "jmac_stream_wait_geq_u32": (c_int, [P, ctypes.c_uint32, P]),
+    "jmac_peer_sum": (c_int, [P, P, c_int, c_int64, c_int64, c_int, P]),
     "jmac_plan_create": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_create_bipartite": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, POINTER(c_void_p)]),
     "jmac_plan_destroy": (c_int, [P]),

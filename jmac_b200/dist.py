@@ -71,6 +71,7 @@ class Shard:
     edge_type: torch.Tensor
     n_edges_global: int
     chunks: int = 1             # row groups of the gathered layout, each exchanged by its own collective
+    peer: object = None         # jmac_b200.peer.PeerExchange: copy-engine exchange over NVLink peer memory instead of NCCL
 
     @property
     def n_loc(self):
@@ -248,6 +249,18 @@ def _default_ops():
     return JF
 
 
+class _EventWait:
+    """``work.wait()`` look-alike over CUDA events: the current stream waits for them."""
+
+    def __init__(self, events):
+        self.events = events
+
+    def wait(self):
+        cur = torch.cuda.current_stream()
+        for ev in self.events:
+            cur.wait_event(ev)
+
+
 class ShardedAttnEdgeFn(torch.autograd.Function):
     """``functional.AttnEdgeFn`` for one destination shard with the exchange fused in and overlapped (see the module
     docstring): forward = chunked all-gather of X || P GEMM, then per chunk Q GEMM as it lands, edge kernel;
@@ -263,8 +276,15 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
         n_loc, d = x_loc.shape
         dev = x_loc.device
         Wt, Wb = W_att[:d], W_att[d:]
+        peer = shard.peer if _DIAG != "nocomm" else None
         if x_full is not None:
             Xf, works = x_full.detach().index_select(0, shard.gather_map(dev)), [None] * shard.chunks
+        elif peer is not None:
+            Xf = torch.empty(shard.n_src, d, dtype=torch.float32, device=dev)
+            works = [_EventWait(evs) for evs in peer.all_gather(x_loc.detach(), Xf)]    # copy-engine pulls, no SM involved
+            if _DIAG == "serial":
+                for w in works:
+                    w.wait()
         else:
             Xf, works = gather_rows(x_loc.detach(), shard, group, async_op=True)
         P = JF.gemm_nn(x_loc, Wt)                                  # runs under the first chunk of the all-gather
@@ -299,7 +319,9 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
         dev = x_loc.device
         G = JF._f32c(g)
         Wt, Wb = W_att[:d], W_att[d:]
-        dP, dXe, dQ = torch.empty_like(x_loc), torch.empty_like(Xf), torch.empty_like(Xf)
+        peer = shard.peer if _DIAG != "nocomm" else None
+        dP, dQ = torch.empty_like(x_loc), torch.empty_like(Xf)
+        dXe = peer.partial_table() if peer is not None else torch.empty_like(Xf)      # peers pull their rows straight out of it
         dRp, dS = torch.empty_like(Rp), torch.empty_like(S)
         acc2 = torch.zeros(2, d, dtype=torch.float32, device=dev)     # [0] = d a_att, [1] = column sums of G over this shard
         da, gsum = acc2[0], acc2[1]
@@ -311,12 +333,17 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
                   "jmac_edge_bwd_src")
         # the partial input gradient of every gathered row, chunk by chunk, each chunk handed to NCCL as soon as it exists
         wb_hi, wb_lo = JF._split_weight(Wb, False)
-        scattered = torch.empty(shard.n_max, d, dtype=torch.float32, device=dev)
+        scattered = torch.empty(shard.n_max, d, dtype=torch.float32, device=dev) if peer is None else None
         works = []
         for c in range(shard.chunks):
             r0, r1 = shard.chunk_rows(c)
             JF._gemm_presplit(dQ[r0:r1], wb_hi, wb_lo, add1=dXe[r0:r1], out=dXe[r0:r1])      # dQ W_bot^T + dXe, in place
-            works.append(scatter_sum_chunk(dXe[r0:r1], scattered[c * shard.n_c:(c + 1) * shard.n_c], shard, group, async_op=True))
+            if peer is not None:
+                peer.scatter_chunk(c)                                                       # handshake + copy-engine pulls of my rows
+                if _DIAG == "serial":
+                    peer.wait_pulls()
+            else:
+                works.append(scatter_sum_chunk(dXe[r0:r1], scattered[c * shard.n_c:(c + 1) * shard.n_c], shard, group, async_op=True))
         # ... under which the rest of the node's backward runs on the compute stream
         with torch.cuda.device(dev):
             check(lib.jmac_edge_bwd_rel(plan.handle, ptr(G), ptr(erec), ptr(a), slope, d, ptr(S), ptr(dRp), ptr(dS), ptr(da), stream_ptr()),
@@ -331,10 +358,13 @@ class ShardedAttnEdgeFn(torch.autograd.Function):
             dWb = JF.gemm_tn(Xf, dQ)
             dWb += JF.small_mm_tn(Rp, dS)
             dW[d:] = dWb
-        for w in works:
-            if w is not None:
-                w.wait()
-        dXd += scattered[:n_loc]
+        if peer is not None:
+            peer.scatter_finish(dXd)                          # waits for the pulls, then dXd += sum over ranks (one kernel)
+        else:
+            for w in works:
+                if w is not None:
+                    w.wait()
+            dXd += scattered[:n_loc]
         return None, dXd, None, dW, dRp, da.view(ctx.a_shape), None, None, None
 
 
@@ -418,6 +448,40 @@ class ShardedEncoder:
         self.plan = self.ops.GraphPlan(self.shard.edge_index, self.shard.edge_type, self.shard.n_loc, num_rel + 1, n_src=self.shard.n_src)
         self.replicated = [p for l in self.layers for p in l.parameters()]
         self._x_loc = None
+        self._setup_peer()
+
+    def _setup_peer(self):
+        """Copy-engine exchange over peer memory (jmac_b200/peer.py) when every rank can set it up; NCCL collectives otherwise.
+        ``JMAC_DIST_PEER=0`` keeps NCCL.  The decision is collective: either every rank uses it or none."""
+        if _backend(self.group) != "nccl" or self.world < 2 or _os.environ.get("JMAC_DIST_PEER", "1") == "0":
+            return
+        d = self.layers[0].in_channels
+        dev = self.shard.edge_index.device
+        ops, sh = self.ops, self.shard
+        if getattr(ops, "attn_edge_eligible", None) is None or not dev.type == "cuda":
+            return
+        mine = (all(l.in_channels == d and l.comp_op == "sub" for l in self.layers) and ops._tc_eligible(sh.n_loc, d, d) and ops._tn_eligible(sh.n_loc, d, d)
+                and ops._tc_eligible(sh.world * sh.n_c, d, d) and ops._tn_eligible(sh.n_src, d, d))
+        vote = torch.tensor([1.0 if mine else 0.0], device=dev)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=self.group)
+        if float(vote.item()) == 0.0:
+            return                                           # some rank would take the composed path: NCCL for everybody
+        from .peer import PeerExchange
+        try:
+            self.shard.peer = PeerExchange(self.shard, d, self.group, dev)
+        except RuntimeError as e:
+            if self.rank == 0:
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL collectives")
+            self.shard.peer = None
+
+    def close(self):
+        """Release the peer-memory buffers (collective in effect: call it on every rank, after the last step has completed)."""
+        peer, self.shard.peer = self.shard.peer, None
+        if peer is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)           # nobody may still be pulling from the buffers freed below
+            peer.close()
 
     def forward(self, x_loc, rel_emb, x_full=None):
         """``x_full``: the replicated input table, if every rank holds it (saves the first all-gather)."""

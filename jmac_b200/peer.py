@@ -9,16 +9,21 @@ CTAs only moved the cost between "exposed communication" and "slower compute".  
   * the all-gather of the layer input is 'every rank PULLS the other ranks' rows' from buffers the owners expose through CUDA IPC;
   * the reduce-scatter of the input-gradient partials is 'every rank pulls ITS slice of every other rank's partial table' into a
     staging buffer, followed by one local sum kernel (a reduction cannot be done by a copy engine);
-  * ordering across processes comes from a tiny NCCL all-reduce on the communication stream before the pulls of a chunk (when it
-    completes on a rank, every rank's producer kernels before it have completed) -- a few microseconds, one channel.
+  * ordering across processes uses no SM either: a rank announces "my producer kernels up to here are done" by copying an epoch
+    number into a flag word of every peer (4-byte copy-engine writes, stream-ordered behind the producer) and waits for its peers
+    with ``cuStreamWaitValue32`` on its own flag words.  (A tiny NCCL all-reduce would do, but its kernel cannot start while
+    every SM is held by a persistent compute CTA -- exactly the stall this module exists to remove.)
 
 Buffers are plain ``cudaMalloc`` allocations of libjmac_b200 (one allocation = one IPC handle), double-buffered per use, and
 wrapped as torch tensors through ``__cuda_array_interface__`` so that the GEMM / edge kernels write straight into them.
+Why two slots are enough: a rank reuses slot s two exchanges later; in between it has passed the handshake of the next exchange,
+which a peer only joins after its own pulls of the previous one were consumed -- so nobody is still reading slot s.
 Setup is collective and all-or-nothing: if any rank cannot allocate or map, every rank falls back to the NCCL path of dist.py.
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional
 
 import torch
@@ -84,7 +89,7 @@ class PeerBuf:
 class PeerExchange:
     """All-gather / reduce-scatter of ``[n_max, d]`` row blocks in the chunk-major gathered layout of ``dist.Shard``."""
 
-    N_STREAMS = 3                                 # pulls are spread over a few streams so that several copy engines work at once
+    N_STREAMS = 4                                 # pulls are spread over a few streams so that several copy engines work at once
 
     def __init__(self, shard, d: int, group, device):
         self.shard, self.d, self.group, self.device = shard, int(d), group, device
@@ -94,10 +99,11 @@ class PeerExchange:
         self.row_bytes = row
         ok = torch.ones(1, device=device)
         self.bufs: List[PeerBuf] = []
+        self.sync_mode = os.environ.get("JMAC_PEER_SYNC", "flags")          # "nccl": a tiny all-reduce instead of the flag handshake (diagnostic)
         try:
-            self.xsrc = [PeerBuf(shard.n_max * row, group, device) for _ in range(2)]
-            self.part = [PeerBuf(shard.n_src * row, group, device) for _ in range(2)]
-            self.bufs = self.xsrc + self.part
+            for nbytes in (shard.n_max * row, shard.n_max * row, shard.n_src * row, shard.n_src * row, 256):
+                self.bufs.append(PeerBuf(nbytes, group, device))
+            self.xsrc, self.part, self.flags = self.bufs[0:2], self.bufs[2:4], self.bufs[4]   # flags: world flag words + one scratch word
         except Exception:
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
@@ -117,7 +123,8 @@ class PeerExchange:
             raise RuntimeError("peer buffers could not be mapped on every rank (no peer access?)")
         with torch.cuda.device(device):
             self.streams = [torch.cuda.Stream(device=device) for _ in range(self.N_STREAMS)]
-            self.flag = torch.zeros(1, device=device)
+            torch.as_tensor(_Raw(self.flags.ptrs[self.rank], (64,), "<i4"), device=device).zero_()
+            self._epoch = 0
             self.x_t = [b.tensor((shard.n_max, self.d)) for b in self.xsrc]
             self.part_t = [b.tensor((shard.n_src, self.d)) for b in self.part]
             for t in self.x_t:
@@ -126,16 +133,49 @@ class PeerExchange:
             torch.cuda.synchronize()
         self._x_slot = 0
         self._p_slot = 0
+        self._nccl_flag = torch.zeros(1, device=device)
         dist.barrier(group=group)
+        # one handshake as a self-test (stream memory operations available, flag words reachable from every peer)
+        try:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self._barrier_then(ev)
+            for s in self.streams:
+                s.synchronize()
+        except Exception:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok.item()) == 0.0:
+            self.close()
+            raise RuntimeError("peer handshake failed: " + self.lib.jmac_last_error().decode())
 
     # ---- plumbing ---------------------------------------------------------------------------------------------------------
     def _barrier_then(self, after_event: torch.cuda.Event):
-        """On stream 0: wait for ``after_event`` (this rank's producer), then a tiny all-reduce: when it completes here, every
-        rank's producer has completed.  The other copy streams wait for it too."""
+        """On stream 0: wait for ``after_event`` (this rank's producer), publish the next epoch to every peer, wait until every
+        peer has published it: from then on every rank's producer has completed.  The other copy streams wait for stream 0."""
         s0 = self.streams[0]
         s0.wait_event(after_event)
-        with torch.cuda.stream(s0):
-            dist.all_reduce(self.flag, group=self.group)
+        if self.sync_mode == "nccl":
+            with torch.cuda.stream(s0):
+                dist.all_reduce(self._nccl_flag, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(s0)
+            for s in self.streams[1:]:
+                s.wait_event(ev)
+            return
+        self._epoch = (self._epoch + 1) & 0xFFFFFFFF
+        st = ctypes.c_void_p(s0.cuda_stream)
+        lib = self.lib
+        mine = self.flags.ptrs[self.rank]
+        word = mine + 4 * self.world                                  # scratch word behind the flag words
+        with torch.cuda.device(self.device):
+            check(lib.jmac_stream_write_u32(ctypes.c_void_p(word), self._epoch, st), "jmac_stream_write_u32")
+            for i in range(1, self.world):
+                g = (self.rank + i) % self.world
+                check(lib.jmac_memcpy_async(ctypes.c_void_p(self.flags.ptrs[g] + 4 * self.rank), ctypes.c_void_p(word), 4, st), "jmac_memcpy_async")
+            for i in range(1, self.world):
+                g = (self.rank + i) % self.world
+                check(lib.jmac_stream_wait_geq_u32(ctypes.c_void_p(mine + 4 * g), self._epoch, st), "jmac_stream_wait_geq_u32")
         ev = torch.cuda.Event()
         ev.record(s0)
         for s in self.streams[1:]:
@@ -143,7 +183,8 @@ class PeerExchange:
 
     def _copy(self, k: int, dst_ptr: int, src_ptr: int, nbytes: int):
         s = self.streams[k % self.N_STREAMS]
-        check(self.lib.jmac_memcpy_async(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), nbytes, ctypes.c_void_p(s.cuda_stream)), "jmac_memcpy_async")
+        with torch.cuda.device(self.device):
+            check(self.lib.jmac_memcpy_async(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), nbytes, ctypes.c_void_p(s.cuda_stream)), "jmac_memcpy_async")
 
     def _done_events(self):
         evs = []
@@ -203,15 +244,32 @@ class PeerExchange:
             self._copy(i, dst, src, chunk_bytes)
         self._pulls.append(self._done_events())
 
-    def scatter_finish(self) -> torch.Tensor:
-        """[n_loc, d]: sum over the ranks of this rank's rows (fixed order: deterministic)."""
+    def wait_pulls(self):
+        main = torch.cuda.current_stream(self.device)
+        for evs in self._pulls:
+            for ev in evs:
+                main.wait_event(ev)
+
+    def scatter_finish(self, acc: torch.Tensor):
+        """acc [n_loc, d] += sum over the ranks of this rank's rows of the partial tables (ranks added in ascending order:
+        deterministic).  The current stream waits for the pulls here, not earlier."""
         sh = self.shard
         main = torch.cuda.current_stream(self.device)
         for evs in self._pulls:
             for ev in evs:
                 main.wait_event(ev)
         self._pulls = []
-        return self.stage.sum(dim=1).reshape(sh.n_max, self.d)[: sh.n_loc]
+        assert acc.is_contiguous() and acc.dtype == torch.float32 and acc.shape == (sh.n_loc, self.d)
+        st = ctypes.c_void_p(main.cuda_stream)
+        per = sh.n_c * self.d
+        with torch.cuda.device(self.device):
+            for c in range(sh.chunks):
+                rows = min(sh.n_c, sh.n_loc - c * sh.n_c)
+                if rows <= 0:
+                    break
+                check(self.lib.jmac_peer_sum(ctypes.c_void_p(acc.data_ptr() + c * per * 4), ctypes.c_void_p(self.stage.data_ptr() + c * self.world * per * 4),
+                                             self.world, per, rows * self.d, 1, st), "jmac_peer_sum")
+        return acc
 
     def close(self):
         for b in self.bufs:
@@ -219,4 +277,7 @@ class PeerExchange:
         self.bufs = []
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -2,8 +2,11 @@
 exchange) against the float64 ORACLE with the gradient budget of SURVEY 8c, the data-parallel completion scorer against
 the single-GPU scorer, and the row-sharded alignment evaluation against the single-GPU one.
 Needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box (bench.py prints the same parity numbers at every N > 1)."""
+import datetime
 import os
 import socket
+import sys
+import traceback
 
 import numpy as np
 import pytest
@@ -20,6 +23,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _die():
+    """A failing rank leaves at once (traceback on stderr, exit code 1) instead of tearing the process group down: the peer may be
+    waiting for it in a collective, and mp.spawn terminates the peer as soon as it sees the exit code."""
+    traceback.print_exc()
+    sys.stderr.flush()
+    os._exit(1)
+
+
 def _make_layers(d):
     from types import SimpleNamespace
     from jmac_b200 import RelationAwareLayer
@@ -31,11 +42,12 @@ def _rel_err(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-def _worker(rank, world, port, N, E, R, d, chunks):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, N, E, R, d, chunks, exchange="nccl"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), JMAC_DIST_PEER="1" if exchange == "peer" else "0",
+                      CUDA_DEVICE_MAX_CONNECTIONS="32")
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     try:
         from jmac_b200 import dist as JD
         from oracle import jmac_oracle as O
@@ -61,36 +73,50 @@ def _worker(rank, world, port, N, E, R, d, chunks):
         # ---- sharded
         layers = [l.to(dev) for l in _make_layers(d)]
         enc = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD, chunks=chunks)
+        assert (enc.shard.peer is not None) == (exchange == "peer")
         rg = rel.to(dev).requires_grad_(True)
         out = enc.step(x.to(dev), rg, gout.to(dev))
+        if exchange == "peer":
+            # the copy-engine exchange moves the same numbers as NCCL's all-gather and adds the partials in rank order: a second and third
+            # step (slot reuse of the double-buffered peer tables) must reproduce the first (up to BatchNorm's fp64 atomics)
+            dx1 = enc._x_loc.grad.clone()
+            for _ in range(2):
+                out2 = enc.step(x.to(dev), rg, gout.to(dev))
+                torch.testing.assert_close(out2, out, rtol=1e-5, atol=1e-6)
+                torch.testing.assert_close(enc._x_loc.grad, dx1, rtol=1e-5, atol=1e-6 * float(dx1.abs().max()))
         sh = enc.shard
         torch.testing.assert_close(out.double(), h64[sh.lo:sh.hi], atol=1e-4, rtol=1e-4)   # two stacked layers; the hub row (sqrt(deg) = 110) amplifies fp32 path differences
 
-        def budget(got, ref64, ref32, name, rows=True):
-            # err(new) <= max(1e-4, 4 x err(reference-fp32)), both measured against the float64 run.  Two stacked layers:
-            # a LeakyReLU sign decision of the second layer that differs from float64 (tests/budget.py) spreads through the first
-            # layer's backward.  Row tables (dX, dR): beyond the budget only a sliver of rows may move, each by a small fraction of
-            # the largest entry; dense parameter gradients (every entry sums over all edges): twice the budget.
-            err_new, err_ref = _rel_err(got, ref64), _rel_err(ref32, ref64)
-            tol = max(1e-4, 4 * err_ref)
-            if err_new <= tol:
-                return
-            if not rows:
-                assert err_new <= 2 * tol, f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}"
-                return
-            a, b = got.double(), ref64.double()
-            row_err = (a - b).abs().reshape(a.shape[0], -1).amax(1) / b.abs().max().clamp_min(1e-30)
-            assert float((row_err > tol).float().mean()) <= 2e-3 and float(row_err.max()) <= 5e-2, \
-                f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}, {int((row_err > tol).sum())} rows out of budget"
+        # ---- the single-GPU CUDA path on the whole graph (validated on its own, sign decision by sign decision, in test_gpu_layer.py)
+        single = [l.to(dev) for l in _make_layers(d)]
+        xs, rs = x.to(dev).requires_grad_(True), rel.to(dev).requires_grad_(True)
+        hs = single[1](single[0](xs, rs, ei, et), rs, ei, et)
+        hs.backward(gout.to(dev))
+        fused = JD._fused_eligible(enc.ops, enc._x_loc, sh, d)
+        # fused path: same kernels, same rows, only BatchNorm's sums are added in another order; composed path (small shards): library GEMMs
+        torch.testing.assert_close(out, hs.detach()[sh.lo:sh.hi], atol=2e-5 if fused else 1e-4, rtol=1e-5 if fused else 1e-4)
 
-        budget(enc._x_loc.grad, dx64[sh.lo:sh.hi], dx32[sh.lo:sh.hi], "dX")
-        budget(rg.grad, dr64, dr32, "dR")
-        for l, pl64, pl32 in zip(layers, p64, p32):
+        def budget(got, ref64, ref32, one_gpu, name):
+            # err(new) <= max(1e-4, 4 x err(reference-fp32)), both measured against the float64 run of the ORACLE.  Two stacked
+            # layers: a LeakyReLU sign decision of the second layer that differs from float64 (tests/budget.py attributes them one by one
+            # for the single-GPU kernels) spreads through the first layer's backward.  Such flips are discrete events and the sharded path's
+            # may be a few others than the single-GPU path's (different BatchNorm summation order, library GEMMs on small shards), so beyond
+            # the budget the sharded path has to stay within twice the larger of the budget and the single-GPU path's own distance from
+            # float64, and within 1e-2 of the single-GPU result itself.
+            err_new, err_ref, err_one = _rel_err(got, ref64), _rel_err(ref32, ref64), _rel_err(one_gpu, ref64)
+            tol = max(1e-4, 4 * err_ref)
+            assert err_new <= tol or err_new <= 2 * max(tol, err_one), f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}, single GPU {err_one:.2e}"
+            assert _rel_err(got, one_gpu) <= 1e-2, f"{name}: {_rel_err(got, one_gpu):.2e} from the single-GPU path"
+
+        budget(enc._x_loc.grad, dx64[sh.lo:sh.hi], dx32[sh.lo:sh.hi], xs.grad[sh.lo:sh.hi], "dX")
+        budget(rg.grad, dr64, dr32, rs.grad, "dR")
+        for l, l1, pl64, pl32 in zip(layers, single, p64, p32):
+            one = dict(l1.named_parameters())
             for k, v in l.named_parameters():
                 if k == "loop_rel":
                     assert float(v.grad.abs().max()) <= 2e-3        # mathematically zero (BatchNorm removes constants): fp32 noise only
                     continue
-                budget(v.grad, pl64[k].grad, pl32[k].grad, k, rows=False)
+                budget(v.grad, pl64[k].grad, pl32[k].grad, one[k].grad, k)
         # ---- data-parallel completion scorer on the sharded encoder output + the replicated input table
         from jmac_b200 import functional as JF
         B, K = 64, 8
@@ -117,8 +143,17 @@ def _worker(rank, world, port, N, E, R, d, chunks):
         torch.testing.assert_close(e1_loc.grad, ref_g[1][sh.lo:sh.hi], rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(rt[0].grad, ref_g[2], rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(rt[1].grad, ref_g[3], rtol=1e-4, atol=1e-6)
-    finally:
-        dist.destroy_process_group()
+        enc.close()
+    except BaseException:
+        _die()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("N,E,chunks", [(12000, 100001, 1), (20000, 150001, 2), (40000, 250001, None)])
+def test_sharded_encoder_peer_exchange_matches_oracle(N, E, chunks):
+    """The same budget with the exchange done by copy-engine pulls over NVLink peer memory (jmac_b200/peer.py)."""
+    mp.spawn(_worker, args=(2, _free_port(), N, E, 30, 256, chunks, "peer"), nprocs=2, join=True)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -134,7 +169,7 @@ def _align_worker(rank, world, port, n1, n2, d, csls):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     try:
         from jmac_b200 import finding as F
         g = torch.Generator(device=dev).manual_seed(3)
@@ -146,8 +181,9 @@ def _align_worker(rank, world, port, n1, n2, d, csls):
         ranks1, top1 = F.alignment_ranks_bf16(A, B, csls_k=csls)                       # this rank alone
         ranks2, top2 = F.alignment_ranks_bf16(A, B, csls_k=csls, group=dist.group.WORLD)  # rows sharded over the ranks
         assert torch.equal(ranks1, ranks2) and torch.equal(top1, top2)                  # same kernels on disjoint rows: bit-identical
-    finally:
-        dist.destroy_process_group()
+    except BaseException:
+        _die()
+    dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
