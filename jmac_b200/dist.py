@@ -427,7 +427,7 @@ def default_chunks(group, n_rows_per_rank: int) -> int:
     if _os.environ.get("JMAC_DIST_CHUNKS"):
         return max(1, int(_os.environ["JMAC_DIST_CHUNKS"]))
     world = dist.get_world_size(group)
-    for c in (4, 2):
+    for c in ((2,) if world > 4 else (4, 2)):           # 8 GPUs: 35.6 ms with 2 chunks, 36.4-36.6 ms with 4 or 8 (profiles/multi_gpu_overlap_r02.md)
         if n_rows_per_rank // c * world >= 8192:
             return c
     return 1
@@ -452,8 +452,11 @@ class ShardedEncoder:
 
     def _setup_peer(self):
         """Copy-engine exchange over peer memory (jmac_b200/peer.py) when every rank can set it up; NCCL collectives otherwise.
-        ``JMAC_DIST_PEER=0`` keeps NCCL.  The decision is collective: either every rank uses it or none."""
-        if _backend(self.group) != "nccl" or self.world < 2 or _os.environ.get("JMAC_DIST_PEER", "1") == "0":
+        Default: up to 4 ranks -- measured on the C4 graph (profiles/multi_gpu_overlap_r02.md): 73.9 vs 77.4 ms at 2 GPUs, 46.6 vs 49.6 ms
+        at 4, but 39.7 vs 36.6 ms at 8, where seven concurrent copy-engine pulls per rank no longer reach NCCL's transfer rate.
+        ``JMAC_DIST_PEER=0`` / ``=1`` forces NCCL / peer memory.  The decision is collective: either every rank uses it or none."""
+        want = _os.environ.get("JMAC_DIST_PEER", "")
+        if _backend(self.group) != "nccl" or self.world < 2 or want == "0" or (want != "1" and self.world > 4):
             return
         d = self.layers[0].in_channels
         dev = self.shard.edge_index.device
