@@ -66,7 +66,7 @@ template <int VPL, int U>
 __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
     typedef typename MaskT<VPL>::type mask_t;
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = __shfl_sync(FULL, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), 0);   // warp-uniform for the compiler
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int d4 = p.d4;
     Row<VPL> av, da_acc, gs_acc;
@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(256) edge_bwd_dst_kernel(EdgeBwdDstParams p) {
 #pragma unroll
                         for (int i = 0; i < VPL; ++i) {
                             const unsigned b = bits[u] >> (4 * i);
-                            mu.v[i].x += (b & 1u) ? ds : 0.f;
-                            mu.v[i].y += (b & 2u) ? ds : 0.f;
-                            mu.v[i].z += (b & 4u) ? ds : 0.f;
-                            mu.v[i].w += (b & 8u) ? ds : 0.f;
+                            if (b & 1u) mu.v[i].x += ds;
+                            if (b & 2u) mu.v[i].y += ds;
+                            if (b & 4u) mu.v[i].z += ds;
+                            if (b & 8u) mu.v[i].w += ds;
                         }
                         if (lane == k + u) { w_keep = w; ds_keep = ds; }
                     }
@@ -232,7 +232,7 @@ template <int VPL, int MODE, int U>
 __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParams p) {
     typedef typename MaskT<VPL>::type mask_t;
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = __shfl_sync(FULL, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), 0);   // warp-uniform for the compiler
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int d4 = p.d4;
     Row<VPL> av, da_acc;
@@ -280,10 +280,10 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
                     for (int i = 0; i < VPL; ++i) {
                         fma4(accw.v[i], w[u], g[u].v[i]);
                         const unsigned b = bits[u] >> (4 * i);
-                        accz.v[i].x += (b & 1u) ? ds[u] : 0.f;
-                        accz.v[i].y += (b & 2u) ? ds[u] : 0.f;
-                        accz.v[i].z += (b & 4u) ? ds[u] : 0.f;
-                        accz.v[i].w += (b & 8u) ? ds[u] : 0.f;
+                        if (b & 1u) accz.v[i].x += ds[u];
+                        if (b & 2u) accz.v[i].y += ds[u];
+                        if (b & 4u) accz.v[i].z += ds[u];
+                        if (b & 8u) accz.v[i].w += ds[u];
                     }
                 }
             }
@@ -412,7 +412,7 @@ template <int VPL, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(EdgeBwdDstParams p) {
     typedef typename MaskT<VPL>::type mask_t;
     extern __shared__ __align__(16) uint8_t ring_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = __shfl_sync(FULL, threadIdx.x >> 5, 0);   // broadcast: lets the compiler see a warp-uniform value
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
@@ -441,6 +441,15 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
             sv = __ldg(p.logit + batch_base + lane);
         }
         float w_keep = 0.f, ds_keep = 0.f;
+        // The relation rows R'[t] of a pair come from L2 (~700 cycles under load) and are needed as soon as the pair's gathered rows are
+        // there: they are loaded one pair ahead (by stream position -- the stream runs across segment boundaries) and carried in registers.
+        // (rows of up to 8 registers; the wider ones would spill, they load at the point of use.)
+        constexpr bool REL_AHEAD = VPL <= 2;
+        Row<REL_AHEAD ? VPL : 1> rn0, rn1;
+        if (REL_AHEAD) {
+            load_row<REL_AHEAD ? VPL : 1, false>(rn0, p.Rp, __shfl_sync(FULL, tv, 0), d4, lane);
+            load_row<REL_AHEAD ? VPL : 1, false>(rn1, p.Rp, __shfl_sync(FULL, tv, 1), d4, lane);
+        }
         for (int it = it0; it < it1; ++it) {
             Item nxt = item;
             if (it + 1 < it1) {
@@ -488,11 +497,18 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
                 }
                 const bool two = k + 1 < item.end;
                 const int kb = k - batch_base, kb1 = two ? kb + 1 : kb;
-                const int t0 = __shfl_sync(FULL, tv, kb), t1 = __shfl_sync(FULL, tv, kb1);
                 const float sc0 = __shfl_sync(FULL, sv, kb), sc1 = __shfl_sync(FULL, sv, kb1);
                 Row<VPL> r0, r1;
-                load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
-                load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
+                if constexpr (REL_AHEAD) {
+                    r0 = rn0;
+                    r1 = rn1;                                     // r1 of an unpaired last edge is some other (finite) row: its weight below is 0
+                    const int nb = kb + (two ? 2 : 1);            // the next pair of the stream; kb < ADV, so nb + 1 < 32 (lanes past the stream hold type 0)
+                    load_row<VPL, false>(rn0, p.Rp, __shfl_sync(FULL, tv, nb), d4, lane);
+                    load_row<VPL, false>(rn1, p.Rp, __shfl_sync(FULL, tv, nb + 1), d4, lane);
+                } else {
+                    load_row<VPL, false>(r0, p.Rp, __shfl_sync(FULL, tv, kb), d4, lane);
+                    load_row<VPL, false>(r1, p.Rp, __shfl_sync(FULL, tv, kb1), d4, lane);
+                }
                 Row<VPL> x0, x1;
                 const uint8_t* sl0 = ring.wait_next();
                 lds_row<VPL>(x0, reinterpret_cast<const float*>(sl0), d4, lane);
@@ -520,13 +536,20 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
                 const float al0 = __expf(sc0 - lse), al1 = two ? __expf(sc1 - lse) : 0.f;
                 const float ds0 = al0 * (c * u0 - gdot), ds1 = al1 * (c * u1 - gdot);
                 ds_sum += ds0 + ds1;
+                // one bit test (predicate) + one predicated add per feature and edge
 #pragma unroll
                 for (int i = 0; i < VPL; ++i) {
-                    const unsigned q0 = b0 >> (4 * i), q1 = b1 >> (4 * i);
-                    mu.v[i].x += ((q0 & 1u) ? ds0 : 0.f) + ((q1 & 1u) ? ds1 : 0.f);
-                    mu.v[i].y += ((q0 & 2u) ? ds0 : 0.f) + ((q1 & 2u) ? ds1 : 0.f);
-                    mu.v[i].z += ((q0 & 4u) ? ds0 : 0.f) + ((q1 & 4u) ? ds1 : 0.f);
-                    mu.v[i].w += ((q0 & 8u) ? ds0 : 0.f) + ((q1 & 8u) ? ds1 : 0.f);
+                    if (b0 & (1u << (4 * i))) mu.v[i].x += ds0;
+                    if (b0 & (2u << (4 * i))) mu.v[i].y += ds0;
+                    if (b0 & (4u << (4 * i))) mu.v[i].z += ds0;
+                    if (b0 & (8u << (4 * i))) mu.v[i].w += ds0;
+                }
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    if (b1 & (1u << (4 * i))) mu.v[i].x += ds1;
+                    if (b1 & (2u << (4 * i))) mu.v[i].y += ds1;
+                    if (b1 & (4u << (4 * i))) mu.v[i].z += ds1;
+                    if (b1 & (8u << (4 * i))) mu.v[i].w += ds1;
                 }
                 if (lane == kb) { w_keep = c * al0; ds_keep = ds0; }
                 if (two && lane == kb + 1) { w_keep = c * al1; ds_keep = ds1; }
@@ -559,7 +582,7 @@ template <int VPL, int MODE, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kernel(EdgeBwdGatherParams p) {
     typedef typename MaskT<VPL>::type mask_t;
     extern __shared__ __align__(16) uint8_t ring_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = __shfl_sync(FULL, threadIdx.x >> 5, 0);   // broadcast: lets the compiler see a warp-uniform value
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
@@ -623,11 +646,21 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_gather_ring_kerne
                 for (int i = 0; i < VPL; ++i) {
                     fma4(accw.v[i], w0, g0.v[i]);
                     fma4(accw.v[i], w1, g1.v[i]);
-                    const unsigned q0 = b0 >> (4 * i), q1 = b1 >> (4 * i);
-                    accz.v[i].x += ((q0 & 1u) ? d0 : 0.f) + ((q1 & 1u) ? d1 : 0.f);
-                    accz.v[i].y += ((q0 & 2u) ? d0 : 0.f) + ((q1 & 2u) ? d1 : 0.f);
-                    accz.v[i].z += ((q0 & 4u) ? d0 : 0.f) + ((q1 & 4u) ? d1 : 0.f);
-                    accz.v[i].w += ((q0 & 8u) ? d0 : 0.f) + ((q1 & 8u) ? d1 : 0.f);
+                }
+                // one bit test (predicate) + one predicated add per feature and edge
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    if (b0 & (1u << (4 * i))) accz.v[i].x += d0;
+                    if (b0 & (2u << (4 * i))) accz.v[i].y += d0;
+                    if (b0 & (4u << (4 * i))) accz.v[i].z += d0;
+                    if (b0 & (8u << (4 * i))) accz.v[i].w += d0;
+                }
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    if (b1 & (1u << (4 * i))) accz.v[i].x += d1;
+                    if (b1 & (2u << (4 * i))) accz.v[i].y += d1;
+                    if (b1 & (4u << (4 * i))) accz.v[i].z += d1;
+                    if (b1 & (8u << (4 * i))) accz.v[i].w += d1;
                 }
             }
         }

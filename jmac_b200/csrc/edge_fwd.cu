@@ -100,7 +100,7 @@ __device__ __forceinline__ void store_mask(void* mask, int edge, unsigned bits, 
 template <int VPL, int U>
 __global__ void __launch_bounds__(256) edge_fwd_kernel(EdgeFwdParams p) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = __shfl_sync(FULL, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), 0);   // warp-uniform for the compiler
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int d4 = p.d4;
     const bool save = p.logit != nullptr;
@@ -249,7 +249,7 @@ template <int VPL, bool FULLROW>
 __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeFwdParams p) {
     extern __shared__ __align__(16) uint8_t ring_raw[];
     constexpr int RING_S = FwdRing<VPL>::S;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = __shfl_sync(FULL, threadIdx.x >> 5, 0);   // broadcast: lets the compiler see a warp-uniform value
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = FULLROW ? VPL * 32 : p.d4;
@@ -286,6 +286,16 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
         tv = __ldg(p.csr_type + batch_base + lane);
     }
     float sc_keep = 0.f;
+    // The relation rows S[t] of a pair come from L2 (~700 cycles under load) and feed the logits as soon as the pair's gathered rows have
+    // landed: they are loaded one pair ahead (by stream position -- the stream runs across segment boundaries) and carried in registers;
+    // the R'[t] rows, first used after the softmax update, are loaded at the top of their own iteration.  (Rows of up to 8 registers;
+    // wider ones would spill and load at the point of use.)
+    constexpr bool REL_AHEAD = VPL <= 2;
+    Row<REL_AHEAD ? VPL : 1> sn0, sn1;
+    if (REL_AHEAD) {
+        load_row<REL_AHEAD ? VPL : 1, false>(sn0, p.S, __shfl_sync(FULL, tv, 0), d4, lane);
+        load_row<REL_AHEAD ? VPL : 1, false>(sn1, p.S, __shfl_sync(FULL, tv, 1), d4, lane);
+    }
 
     for (int it = it0; it < it1; ++it) {
         // next segment's descriptor and P row are fetched while this one is processed
@@ -345,8 +355,16 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
             const int t0 = __shfl_sync(FULL, tv, kb);
             const int t1 = __shfl_sync(FULL, tv, two ? kb + 1 : kb);
             Row<VPL> s0, r0, s1, r1;
-            load_row<VPL, false>(s0, p.S, t0, d4, lane);
-            load_row<VPL, false>(s1, p.S, t1, d4, lane);
+            if constexpr (REL_AHEAD) {
+                s0 = sn0;
+                s1 = sn1;                                         // s1 of an unpaired last edge is some other (finite) row: its logit is replaced by -inf below
+                const int nb = kb + (two ? 2 : 1);                // the next pair of the stream; kb < ADV, so nb + 1 < 32 (lanes past the stream hold type 0)
+                load_row<VPL, false>(sn0, p.S, __shfl_sync(FULL, tv, nb), d4, lane);
+                load_row<VPL, false>(sn1, p.S, __shfl_sync(FULL, tv, nb + 1), d4, lane);
+            } else {
+                load_row<VPL, false>(s0, p.S, t0, d4, lane);
+                load_row<VPL, false>(s1, p.S, t1, d4, lane);
+            }
             load_row<VPL, false>(r0, p.Rp, t0, d4, lane);
             load_row<VPL, false>(r1, p.Rp, t1, d4, lane);
             const uint32_t sa = use_slot, sb = sa + 1 == RING_S ? 0 : sa + 1;
