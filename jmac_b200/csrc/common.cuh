@@ -190,6 +190,14 @@ __device__ __forceinline__ void bulk_row(uint32_t dst, const float* src, uint32_
                  : "memory");
 }
 
+// Pull the cache lines that hold entry `pos` of up to three 4-byte-per-entry streams (index lists, logits) from HBM towards L2:
+// nothing prefetches sequential streams in hardware, and a warp consumes ~20 entries of each per batch, so without this every
+// batch load pays the full DRAM latency.  Lanes 0..2 issue one prefetch each; `pos` >= n is ignored.
+__device__ __forceinline__ void prefetch_idx_l2(const void* a, const void* b, const void* c, long long pos, long long n, int lane) {
+    const void* t = lane == 0 ? a : (lane == 1 ? b : c);
+    if (lane < 3 && t != nullptr && pos < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(t) + pos * 4));
+}
+
 template <int VPL>
 __device__ __forceinline__ void lds_row(Row<VPL>& r, const float* base, int d4, int lane) {
     const float4* p = reinterpret_cast<const float4*>(base);

@@ -440,6 +440,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
             tv = __ldg(p.csr_type + batch_base + lane);
             sv = __ldg(p.logit + batch_base + lane);
         }
+        prefetch_idx_l2(p.csr_src, p.csr_type, p.logit, batch_base + 32, stream_end, lane);
+        prefetch_idx_l2(p.csr_src, p.csr_type, p.logit, batch_base + 64, stream_end, lane);
         float w_keep = 0.f, ds_keep = 0.f;
         // The relation rows R'[t] of a pair come from L2 (~700 cycles under load) and are needed as soon as the pair's gathered rows are
         // there: they are loaded one pair ahead (by stream position -- the stream runs across segment boundaries) and carried in registers.
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
                         tv = __ldg(p.csr_type + batch_base + lane);
                         sv = __ldg(p.logit + batch_base + lane);
                     }
+                    prefetch_idx_l2(p.csr_src, p.csr_type, p.logit, batch_base + 96, stream_end, lane);   // a batch advances < 32 entries: every line is covered
                 }
                 const int want = min(stream_end, k + BWD_RING_S);
                 while (issued + 1 < want) {                      // warp-uniform; steady state: one pair per iteration

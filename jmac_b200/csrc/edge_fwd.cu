@@ -285,6 +285,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
         jv = __ldg(p.csr_src + batch_base + lane);
         tv = __ldg(p.csr_type + batch_base + lane);
     }
+    prefetch_idx_l2(p.csr_src, p.csr_type, nullptr, batch_base + 32, stream_end, lane);
+    prefetch_idx_l2(p.csr_src, p.csr_type, nullptr, batch_base + 64, stream_end, lane);
     float sc_keep = 0.f;
     // The relation rows S[t] of a pair come from L2 (~700 cycles under load) and feed the logits as soon as the pair's gathered rows have
     // landed: they are loaded one pair ahead (by stream position -- the stream runs across segment boundaries) and carried in registers;
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
                     jv = __ldg(p.csr_src + batch_base + lane);
                     tv = __ldg(p.csr_type + batch_base + lane);
                 }
+                prefetch_idx_l2(p.csr_src, p.csr_type, nullptr, batch_base + 96, stream_end, lane);       // a batch advances < 32 entries: every line is covered
             }
             // keep the ring full: issue the Q[j], X[j] gathers up to position k + RING_S - 1 (may belong to later segments)
             const int want = min(stream_end, k + RING_S);
