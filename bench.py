@@ -887,11 +887,18 @@ def run_b200(args):
             outs = []
             prefetch(slots[0])
             for i in range(n):
+                t0 = time.perf_counter()
                 loss = compute(slots[i % 2])                         # enqueued asynchronously ...
+                t1 = time.perf_counter()
                 if i + 1 < n:
                     prefetch(slots[(i + 1) % 2])                     # ... so the next upload + plan build (host-synchronising) overlap it
+                t2 = time.perf_counter()
                 outs.append(float(loss.item()))
+                t3 = time.perf_counter()
                 JF.clear_plan_cache()
+                if trace and rank == 0:
+                    print(f"e2e pipelined step {i}: host ms enqueue {1e3 * (t1 - t0):.1f}, prefetch+plan {1e3 * (t2 - t1):.1f}, wait for loss {1e3 * (t3 - t2):.1f}",
+                          file=sys.stderr)
             return outs
         pipelined(2)
         torch.cuda.synchronize()

@@ -9,6 +9,14 @@
 
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include "common.cuh"
 
 namespace jmac {
@@ -51,31 +59,124 @@ int sm_count() {
     return n - r > 8 ? n - r : n;
 }
 
-// Stream-ordered allocation for the plan and its build temporaries: cudaMalloc / cudaFree serialise the device and
-// cost milliseconds per 100 MB block, which made rebuilding a 40M-edge plan (a triple-transfer round, train.py:471-472,
-// or the host-fed bench step) slower than the sorts themselves.  The default memory pool keeps freed blocks
-// (release threshold = max), so a rebuilt plan reuses the memory of the destroyed one without touching the OS.
-// Bounded: at most 8 GiB of freed plan memory stay cached per device (a C4 plan with its sort temporaries is ~4 GB); beyond that
-// the pool hands memory back at the next synchronisation, so PyTorch's allocator is not starved.  Set once per device.
-static void pool_setup() {
-    static unsigned long long done_mask = 0;       // bit per device ordinal (< 64)
+// Stream-ordered allocation for the plan and its build temporaries, from a block cache owned by the library.
+// cudaMalloc / cudaFree serialise the device and cost milliseconds per 100 MB block, which made rebuilding a 40M-edge plan (a
+// triple-transfer round, train.py:471-472, or the host-fed bench step) slower than the sorts themselves.  The driver's own pool
+// (cudaMallocAsync) removes that in the common case but trims and re-grows itself at synchronisation points: intermittent 0.2-0.8 s
+// host stalls in the two-deep host-fed pipeline (bench.py e2e: 127 / 144 / 191 / 289 ms per step, run to run).  So freed blocks
+// are kept here: a free records an event on the freeing stream, a later allocation of a similar size on ANY stream takes the
+// block and makes its stream wait for that event on the device -- no host wait, no driver allocation after the first build of a
+// given graph size.  Bounded: at most 32 GiB (JMAC_POOL_KEEP_GIB) of free blocks stay cached per device, beyond that the largest
+// ones go back to the driver.  While a stream is being captured into a CUDA graph the driver's stream-ordered allocator is used
+// (its nodes can be captured; events recorded outside the capture cannot be waited for inside it).
+namespace {
+struct Block { void* ptr; size_t bytes; cudaEvent_t ev; bool pool; };
+struct DevCache {
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    std::unordered_map<void*, Block> live;
+    size_t cached = 0;
+};
+DevCache* dev_cache() {
+    static DevCache caches[64];
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-    const unsigned long long bit = 1ULL << dev;
-    if (__atomic_fetch_or(&done_mask, bit, __ATOMIC_RELAXED) & bit) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = 8ULL << 30;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return &caches[dev];
+}
+size_t cache_cap() {
+    static const size_t cap = [] {
+        const char* env = getenv("JMAC_POOL_KEEP_GIB");
+        const long gib = env ? atol(env) : 32;
+        return (size_t)(gib > 0 ? gib : 1) << 30;
+    }();
+    return cap;
+}
+bool capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs != cudaStreamCaptureStatusNone;
+}
+void drop_block(const Block& b) {          // back to the driver (host-synchronous: only when the cache is over its bound or out of memory)
+    cudaEventSynchronize(b.ev);
+    cudaFree(b.ptr);
+    cudaEventDestroy(b.ev);
+}
+}  // namespace
+
+static cudaError_t dmalloc_bytes(void** p, size_t bytes, cudaStream_t st) {
+    const size_t need = ((bytes > 0 ? bytes : 1) + 511) & ~(size_t)511;
+    DevCache* dc = dev_cache();
+    if (capturing(st)) {
+        cudaError_t e = cudaMallocAsync(p, need, st);
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> g(dc->mu);
+            dc->live[*p] = Block{*p, need, nullptr, true};
+        }
+        return e;
     }
+    std::lock_guard<std::mutex> g(dc->mu);
+    int best = -1;
+    for (int i = 0; i < (int)dc->free_blocks.size(); ++i) {
+        const size_t b = dc->free_blocks[i].bytes;
+        if (b >= need && b <= need + need / 4 + (1u << 20) && (best < 0 || b < dc->free_blocks[best].bytes)) best = i;
+    }
+    if (best >= 0) {
+        Block blk = dc->free_blocks[best];
+        dc->free_blocks.erase(dc->free_blocks.begin() + best);
+        dc->cached -= blk.bytes;
+        cudaError_t e = cudaStreamWaitEvent(st, blk.ev, 0);      // the block's previous user (any stream) finishes first -- on the device
+        if (e != cudaSuccess) { drop_block(blk); return e; }
+        dc->live[blk.ptr] = blk;
+        *p = blk.ptr;
+        return cudaSuccess;
+    }
+    Block blk{nullptr, need, nullptr, false};
+    cudaError_t e = cudaMalloc(&blk.ptr, need);
+    if (e != cudaSuccess) {                                       // out of memory: give the cached blocks back and retry once
+        cudaGetLastError();
+        for (const Block& b : dc->free_blocks) drop_block(b);
+        dc->free_blocks.clear();
+        dc->cached = 0;
+        e = cudaMalloc(&blk.ptr, need);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFree(blk.ptr); return e; }
+    dc->live[blk.ptr] = blk;
+    *p = blk.ptr;
+    return cudaSuccess;
 }
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t bytes, cudaStream_t st) {
-    pool_setup();
-    return cudaMallocAsync(reinterpret_cast<void**>(p), bytes > 0 ? bytes : 1, st);
+    return dmalloc_bytes(reinterpret_cast<void**>(p), bytes, st);
 }
 static void dfree(void* p, cudaStream_t st) {
-    if (p) cudaFreeAsync(p, st);
+    if (!p) return;
+    DevCache* dc = dev_cache();
+    std::lock_guard<std::mutex> g(dc->mu);
+    auto it = dc->live.find(p);
+    if (it == dc->live.end()) return;                             // not ours (cannot happen): leave it alone
+    Block blk = it->second;
+    dc->live.erase(it);
+    if (blk.pool) { cudaFreeAsync(p, st); return; }
+    if (capturing(st) || cudaEventRecord(blk.ev, st) != cudaSuccess) {   // cannot be ordered by an event: hand it back synchronously
+        cudaGetLastError();
+        cudaStreamSynchronize(st);
+        cudaFree(blk.ptr);
+        cudaEventDestroy(blk.ev);
+        return;
+    }
+    dc->free_blocks.push_back(blk);
+    dc->cached += blk.bytes;
+    while (dc->cached > cache_cap() && !dc->free_blocks.empty()) {
+        int big = 0;
+        for (int i = 1; i < (int)dc->free_blocks.size(); ++i)
+            if (dc->free_blocks[i].bytes > dc->free_blocks[big].bytes) big = i;
+        Block d = dc->free_blocks[big];
+        dc->free_blocks.erase(dc->free_blocks.begin() + big);
+        dc->cached -= d.bytes;
+        drop_block(d);
+    }
 }
 // Build temporaries of one scope: returned to the pool (stream-ordered) when the scope ends, including on the
 // early-return error paths of JMAC_CUDA / JMAC_LAUNCH_CHECK.
@@ -301,8 +402,8 @@ extern "C" int jmac_status_poll(void) {
 extern "C" int jmac_plan_destroy(jmac_plan* p) {
     if (!p) return 0;
     // No host-side wait: the frees are stream-ordered on a per-device "free" stream that first waits for the last kernel that read
-    // the plan on every stream it was used on (plan_mark_use).  The memory goes back to the pool (not to the OS), so a rebuilt plan
-    // reuses it.  Only a plan used from more than four streams falls back to one device-wide wait.
+    // the plan on every stream it was used on (plan_mark_use).  The memory goes back to the library's block cache (not to the driver),
+    // so a rebuilt plan reuses it.  Only a plan used from more than four streams falls back to one device-wide wait.
     int cur = p->device;
     cudaGetDevice(&cur);
     if (cur != p->device) cudaSetDevice(p->device);      // a process that drives several devices may destroy the plan from another one
@@ -315,10 +416,7 @@ extern "C" int jmac_plan_destroy(jmac_plan* p) {
                     p->typ_pos, p->typ_dst, p->dst_items.items, p->dst_items.splits, p->src_items.items, p->src_items.splits,
                     p->typ_items.items, p->typ_items.splits, p->scratch};
     for (void* q : ptrs) dfree(q, fs);
-    // Wait for the free stream only, i.e. for the plan's own last uses (normally long finished), NOT for the device: a completed free
-    // is immediately reusable by cudaMallocAsync on any stream -- a pending one would make the next plan build fetch fresh memory from
-    // the OS (measured: +50 ms per rebuild when plans are built on a copy stream while another step computes).
-    if (fs) cudaStreamSynchronize(fs);
+    // No wait at all: each block carries the event recorded on the free stream; whoever takes it from the cache waits for it on the device.
     for (int i = 0; i < p->n_use; ++i) cudaEventDestroy(p->use_ev[i]);
     if (cur != p->device) cudaSetDevice(cur);
     delete p;
