@@ -187,7 +187,7 @@ int jmac_row_normalize_bwd(const float* y, const float* inv, const float* g, int
 /* ------------------------------------------------------------------------------------------
  * Node-level dense product with fp32 accuracy on the tensor cores (3xTF32 split, tcgen05):
  *   C[M,N] = A[M,K] . B[N,K]^T,  B given pre-split: B_hi = B with the low 13 mantissa bits cleared,
- *   B_lo = B - B_hi.  N % 32 == 0, N <= 256, K % 16 == 0; lda/ldb/ldc in elements (multiples of 4).
+ *   B_lo = B - B_hi.  N % 32 == 0, N <= 512 (computed as column parts of <= 256), K % 16 == 0; lda/ldb/ldc in elements (multiples of 4).
  * Replaces the fp32 library GEMMs of the hoisted per-edge products of src/jmac_model.py:75-76,88
  * (P = X W_top, Q = X W_bot, pre = T W_g) and their input-gradient transposes.
  * ------------------------------------------------------------------------------------------ */
@@ -204,7 +204,8 @@ int jmac_gemm_tf32x3_add(const float* A, int64_t lda, const float* B_hi, const f
                          int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K, const float* D1,
                          const float* D2, int64_t ldd, void* stream);
 /* Weight-gradient product D[KO,N] = X[M,KO]^T . G[M,N] (reduction over the M node rows), same
- * 3xTF32 scheme with both operands split in shared memory; KO in {128,256}, N % 32 == 0, N <= 256.
+ * 3xTF32 scheme with both operands split in shared memory; KO % 32 == 0, KO <= 256, N % 32 == 0, N <= 256 (wider tables: one call
+ * per column block of X and of G, jmac_b200.functional.gemm_tn).
  * Deterministic: per-CTA partials in `workspace` (jmac_gemm_tn_workspace_bytes) summed in order. */
 size_t jmac_gemm_tn_workspace_bytes(int KO, int N);
 int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, int64_t ldg, float* D, int64_t M,

@@ -1,5 +1,5 @@
 // Node-level dense products of the GNN layer at tensor-core speed with fp32 accuracy:
-//     C[M,N] = A[M,K] . B[N,K]^T        (fp32 in / out, N <= 256, K % 16 == 0)
+//     C[M,N] = A[M,K] . B[N,K]^T        (fp32 in / out, N <= 512 (column parts of <= 256), K % 16 == 0)
 // computed as three tcgen05 kind::tf32 products (3xTF32 split, error ~2^-21):
 //     A = A_hi + A_lo,  B = B_hi + B_lo  (hi = top 19 bits),   C ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.
 // Replaces the fp32 SIMT library GEMMs behind torch.mm for  P = X W_top, Q = X W_bot,
@@ -316,7 +316,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
 }
 
 struct GemmTnParams {
-    int M, KO, N;            // KO in {128, 256}, N % 32 == 0
+    int M, KO, N;            // KO % 32 == 0, KO <= 256, N % 32 == 0, N <= 256
     int rows_per_cta;        // multiple of T_BR
     float* partial;          // [gridDim.x, KO, N]
 };
@@ -365,7 +365,7 @@ gemm_tf32x3_tn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         if (lane == 0 && nst > 0) {
             // kind::tf32, A and B both MN-major (bits 15, 16), M = 128, N = p.N
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const int halves = p.KO / 128;
+            const int halves = (p.KO + 127) / 128;             // a partial last half multiplies stale shared-memory rows: those accumulator rows are never written out
             for (int it = 0; it < nst; ++it) {
                 const uint32_t s = it % G_NS, ph = (it / G_NS) & 1;
                 const uint32_t st = base + s * T_STAGE;
@@ -417,7 +417,7 @@ gemm_tf32x3_tn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         }
         // ---- partial [KO, N] of this CTA -> global
         float* prow = p.partial + ((size_t)blockIdx.x * p.KO + half * 128 + quarter * 32 + lane) * p.N;
-        const bool active = half * 128 < p.KO;
+        const bool active = half * 128 + quarter * 32 + lane < p.KO;
         if (nst > 0) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
@@ -512,7 +512,7 @@ extern "C" size_t jmac_gemm_tn_workspace_bytes(int KO, int N) { return (size_t)s
 extern "C" int jmac_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* G, int64_t ldg, float* D, int64_t M, int KO, int N,
                                    float* workspace, void* stream) {
     JMAC_ARG(X && G && D && workspace && M > 0 && M < (int64_t(1) << 31));
-    JMAC_ARG((KO == 128 || KO == 256) && N >= 32 && N <= 256 && (N % 32) == 0);
+    JMAC_ARG(KO >= 32 && KO <= 256 && (KO % 32) == 0 && N >= 32 && N <= 256 && (N % 32) == 0);
     JMAC_ARG(ldx >= KO && ldg >= N && (ldx % 4) == 0 && (ldg % 4) == 0);
     JMAC_ARG(((uintptr_t)X % 16) == 0 && ((uintptr_t)G % 16) == 0 && ((uintptr_t)D % 16) == 0 && ((uintptr_t)workspace % 16) == 0);
     CUtensorMap map_x, map_g;
@@ -551,15 +551,22 @@ extern "C" int jmac_gemm_tf32x3_add(const float* A, int64_t lda, const float* B_
     JMAC_ARG(A && B_hi && B_lo && C && M > 0 && M < (int64_t(1) << 31));
     JMAC_ARG(D2 == nullptr || D1 != nullptr);
     JMAC_ARG(D1 == nullptr || (ldd >= N && (ldd % 8) == 0 && ((uintptr_t)D1 % 32) == 0 && ((uintptr_t)D2 % 32) == 0));
-    JMAC_ARG(N >= 32 && N <= 256 && (N % 32) == 0 && K >= 16 && (K % 16) == 0);
+    JMAC_ARG(N >= 32 && N <= 512 && (N % 32) == 0 && K >= 16 && (K % 16) == 0);
     JMAC_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 8) == 0);      // C, D: 256-bit row accesses
     JMAC_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)B_lo % 16) == 0 && ((uintptr_t)C % 32) == 0);
     // few row blocks (the reference's graph sizes: 5-14 k nodes = 20-55 blocks of 256 rows): share every block among 2 or 4
     // CTAs, each computing N/2 or N/4 output columns, so that the launch covers the machine
+    // Wide outputs (N > 256, e.g. JMAC_DBPv1's d = 300 padded to 320) always take the column split: a CTA's two accumulators hold
+    // at most 256 columns each.
     const int n_mb = (int)((M + G_BM - 1) / G_BM);
-    int nsplit = 1;
-    if (n_mb * 4 <= sm_count() && (N % 128) == 0) nsplit = 4;
-    else if (n_mb * 2 <= sm_count() && (N % 64) == 0) nsplit = 2;
+    const int want = n_mb * 4 <= sm_count() ? 4 : (n_mb * 2 <= sm_count() ? 2 : 1);
+    int nsplit = 0;
+    for (int ns = 1; ns <= 16; ++ns) {
+        if (N % ns != 0 || (N / ns) % 32 != 0 || N / ns > 256) continue;
+        nsplit = ns;                      // the smallest legal split ...
+        if (ns >= want) break;            // ... that also covers the machine
+    }
+    JMAC_ARG(nsplit > 0);
     const int Nc = N / nsplit;
     CUtensorMap map_a, map_bhi, map_blo;
     int rc = make_map_f32(&map_a, A, M, K, lda, G_BM);

@@ -379,9 +379,23 @@ def gemm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     M, KO = X.shape
     N = G.shape[1]
     D = torch.empty(KO, N, dtype=torch.float32, device=X.device)
-    ws = torch.empty(int(lib.jmac_gemm_tn_workspace_bytes(KO, N)) // 4, dtype=torch.float32, device=X.device)
+    if KO <= 256 and N <= 256:
+        ws = torch.empty(int(lib.jmac_gemm_tn_workspace_bytes(KO, N)) // 4, dtype=torch.float32, device=X.device)
+        with torch.cuda.device(X.device):
+            check(lib.jmac_gemm_tn_tf32x3(ptr(X), KO, ptr(G), N, ptr(D), M, KO, N, ptr(ws), stream_ptr()), "jmac_gemm_tn_tf32x3")
+        return D
+    # wider tables (JMAC_DBPv1's d = 300 runs at the padded width 320): one launch per block of <= 256 columns of X and of G
+    # (strided views of the row-major tables), each writing its own [KOb, Nb] block
+    ws = torch.empty(int(lib.jmac_gemm_tn_workspace_bytes(256, 256)) // 4, dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
-        check(lib.jmac_gemm_tn_tf32x3(ptr(X), KO, ptr(G), N, ptr(D), M, KO, N, ptr(ws), stream_ptr()), "jmac_gemm_tn_tf32x3")
+        for k0 in range(0, KO, 256):
+            kb = min(256, KO - k0)
+            for n0 in range(0, N, 256):
+                nb = min(256, N - n0)
+                blk = torch.empty(kb, nb, dtype=torch.float32, device=X.device)
+                check(lib.jmac_gemm_tn_tf32x3(X.data_ptr() + 4 * k0, KO, G.data_ptr() + 4 * n0, N, ptr(blk), M, kb, nb, ptr(ws), stream_ptr()),
+                      "jmac_gemm_tn_tf32x3")
+                D[k0:k0 + kb, n0:n0 + nb] = blk
     return D
 
 
@@ -415,11 +429,17 @@ def small_mm_tn(X: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
 
 
 def _tn_eligible(M, KO, N) -> bool:
-    return M >= _TC_MIN_ROWS and KO in (128, 256) and N % 32 == 0 and 32 <= N <= 256
+    return M >= _TC_MIN_ROWS and KO % 32 == 0 and 32 <= KO <= 512 and N % 32 == 0 and 32 <= N <= 512
 
 
 def _tc_eligible(M, K, N) -> bool:
-    return M >= _TC_MIN_ROWS and N % 32 == 0 and 32 <= N <= 256 and K % 16 == 0 and K >= 16
+    return M >= _TC_MIN_ROWS and N % 32 == 0 and 32 <= N <= 512 and K % 16 == 0 and K >= 16
+
+
+def padded_width(d: int) -> int:
+    """Feature width the tensor-core node products and the edge kernels run at for a layer of width ``d``: the next multiple of
+    32 (JMAC_DBPv1's d = 300 -> 320); zero columns stay exactly zero through the layer (zero weight rows / columns, zero BN affine)."""
+    return (int(d) + 31) // 32 * 32
 
 
 class NodeMatmulFn(torch.autograd.Function):

@@ -78,22 +78,45 @@ class RelationAwareLayer(nn.Module):
         Rp = self.relation_transform(rel_emb)                                    # [nr+1, d]; row nr = self loop
         plan = JF.get_plan(edge_index, edge_type, num_ent, Rp.size(0))
         X = ent_emb.contiguous()
-        if JF.attn_edge_eligible(X, d):
+        w_att, a_att, gcn = self.w_att, self.a_att, self.gcn_weight
+        bn_w, bn_b, run_m, run_v = self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var
+        # Widths that are not a multiple of 32 (JMAC_DBPv1: d = 300, JMAC_DBPv1/main_with_args.py:36) run at the next multiple of 32 so
+        # that the node products stay on the tensor cores: zero columns / weight rows / BN affine entries are appended (autograd slices
+        # the gradients back), the padded columns stay exactly zero through the layer, and the result is cut back to d columns.
+        dp = JF.padded_width(d)
+        pad = dp - d if (dp != d and dp <= 512 and X.is_cuda and X.dtype == torch.float32 and num_ent >= JF._TC_MIN_ROWS
+                         and self.dist_group is None) else 0
+        if pad:
+            X, Rp = F.pad(X, (0, pad)), F.pad(Rp, (0, pad))
+            w_att = torch.cat([F.pad(w_att[:d], (0, pad, 0, pad)), F.pad(w_att[d:], (0, pad, 0, pad))], dim=0)
+            a_att, gcn = F.pad(a_att, (0, 0, 0, pad)), F.pad(gcn, (0, pad, 0, pad))
+            bn_w = F.pad(bn_w, (0, pad)) if bn_w is not None else None
+            bn_b = F.pad(bn_b, (0, pad)) if bn_b is not None else None
+            run_m = F.pad(run_m, (0, pad)) if run_m is not None else None                 # temporaries: the kernel updates them in place
+            run_v = F.pad(run_v, (0, pad), value=1.0) if run_v is not None else None
+        dw = d + pad
+        if JF.attn_edge_eligible(X, dw):
             # large node tables: one autograd node for the attention inputs + edge phase, so that the input gradient
             # dP W_top^T + dQ W_bot^T + dXe + dT is accumulated in GEMM epilogues instead of elementwise passes
-            T = JF.attn_edge(plan, X, self.w_att, Rp, self.a_att, self.leaky_slope)
+            T = JF.attn_edge(plan, X, w_att, Rp, a_att, self.leaky_slope)
         else:
-            P = JF.node_mm(X, self.w_att[:d])       # node tables: 3xTF32 tcgen05 GEMM (fp32-accurate), small ones: library
-            Q = JF.node_mm(X, self.w_att[d:])
-            S = torch.mm(Rp, self.w_att[d:])
-            T = JF.edge_phase(plan, P, Q, X, S, Rp, self.a_att, self.leaky_slope, X)  # agg + X - R'[loop] (self-loop fused)
-        pre = JF.node_mm(T, self.gcn_weight * 0.5)                               # (neigh + self)/2, :49-52
+            P = JF.node_mm(X, w_att[:dw])           # node tables: 3xTF32 tcgen05 GEMM (fp32-accurate), small ones: library
+            Q = JF.node_mm(X, w_att[dw:])
+            S = torch.mm(Rp, w_att[dw:])
+            T = JF.edge_phase(plan, P, Q, X, S, Rp, a_att, self.leaky_slope, X)     # agg + X - R'[loop] (self-loop fused)
+        pre = JF.node_mm(T, gcn * 0.5)                                           # (neigh + self)/2, :49-52
         training = self.training or not self.bn.track_running_stats
         if self.training and self.bn.track_running_stats:
             self.bn.num_batches_tracked += 1
         momentum = self.bn.momentum if self.bn.momentum is not None else 0.1
-        return JF.bn_tanh(pre, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var, momentum, self.bn.eps,
-                          training, self.dist_group)
+        out = JF.bn_tanh(pre, bn_w, bn_b, run_m, run_v, momentum, self.bn.eps, training, self.dist_group)
+        if pad:
+            if self.training and self.bn.track_running_stats and run_m is not None:
+                with torch.no_grad():
+                    self.bn.running_mean.copy_(run_m[:d])
+                    self.bn.running_var.copy_(run_v[:d])
+            out = out[:, :d].contiguous()
+        return out
 
 
     def forward_mult(self, ent_emb, rel_emb, edge_index, edge_type):

@@ -31,8 +31,15 @@ def kink_rows(layer, x, r, ei, et):
     with torch.no_grad():
         Rp = layer.relation_transform(r)
         Wt, Wb = layer.w_att[:d], layer.w_att[d:]
-        P, Q = JF.node_mm(x, Wt), JF.node_mm(x, Wb)                     # the same kernels (deterministic) the layer ran
-        S = torch.mm(Rp, Wb)
+        pad = JF.padded_width(d) - d
+        if pad and x.shape[0] >= JF._TC_MIN_ROWS and d + pad <= 512:    # the layer ran zero-padded at the next multiple of 32 (model.py)
+            F = torch.nn.functional
+            xp, Wtp, Wbp = F.pad(x, (0, pad)), F.pad(Wt, (0, pad, 0, pad)), F.pad(Wb, (0, pad, 0, pad))
+            P, Q = JF.node_mm(xp, Wtp)[:, :d], JF.node_mm(xp, Wbp)[:, :d]
+            S = torch.mm(F.pad(Rp, (0, pad)), Wbp)[:, :d]
+        else:
+            P, Q = JF.node_mm(x, Wt), JF.node_mm(x, Wb)                 # the same kernels (deterministic) the layer ran
+            S = torch.mm(Rp, Wb)
         i, j, t = ei[0], ei[1], et
         nz = S[t] - (P[i] + Q[j])                                       # the edge kernels' own operation order (edge_fwd.cu: leaky_dot)
         pos = nz < 0

@@ -12,7 +12,8 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize("M,K,N", [(5000, 256, 256), (4097, 64, 128), (300, 256, 32), (70000, 256, 256), (1000, 16, 96), (257, 128, 224),
-                                   (14000, 256, 256), (13176, 256, 192)])      # DBP-5L node counts: row blocks shared by 2 CTAs (N / 2 columns each)
+                                   (14000, 256, 256), (13176, 256, 192),       # DBP-5L node counts: row blocks shared by 2 CTAs (N / 2 columns each)
+                                   (5000, 320, 320), (70000, 320, 320), (4100, 304, 512), (300, 48, 288)])   # N > 256: always column parts (d = 300 padded to 320)
 def test_gemm_tf32x3_matches_fp64(M, K, N):
     from jmac_b200 import functional as JF
     torch.manual_seed(M + N)
@@ -26,7 +27,8 @@ def test_gemm_tf32x3_matches_fp64(M, K, N):
     assert relerr(C, ref) < 5e-6
 
 
-@pytest.mark.parametrize("M,KO,N", [(5000, 256, 256), (4099, 128, 96), (70001, 256, 32), (16, 256, 256), (40000, 128, 256)])
+@pytest.mark.parametrize("M,KO,N", [(5000, 256, 256), (4099, 128, 96), (70001, 256, 32), (16, 256, 256), (40000, 128, 256),
+                                    (5000, 64, 160), (4099, 224, 32), (5000, 320, 320), (20000, 512, 288)])   # partial 128-row halves; column blocks
 def test_gemm_tn_tf32x3_matches_fp64(M, KO, N):
     """Weight-gradient product X^T G (MN-major operands, split-M partials, deterministic)."""
     from jmac_b200 import functional as JF

@@ -144,6 +144,8 @@ def oracle_run(layer, ei, et, x, r, gout, dtype, training=True, comp_op="sub"):
     (33, 1, 2, 256, 0),               # a single edge
     (5000, 30001, 40, 256, 2000),     # >= 4096 nodes: the fused attention-input node (tcgen05 GEMMs, epilogue gradient accumulation)
     (4200, 9000, 7, 128, 0),
+    (5000, 30001, 40, 300, 2000),     # JMAC_DBPv1 width on >= 4096 nodes: runs zero-padded at 320 on the tensor-core path (N = 320: column parts)
+    (4500, 20000, 12, 200, 0),        # ... and 200 -> 224
     (50, 0, 4, 32, 0),                # E = 0: every node is isolated
 ])
 def test_layer_matches_oracle_fp64_budget(N, E, R, d, hub):
