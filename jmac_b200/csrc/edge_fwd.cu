@@ -307,6 +307,13 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_fwd_ring_kernel(EdgeF
         if (it + 1 < it1) {
             nxt = p.items[it + 1];
             load_row<VPL, true>(pn, p.P, nxt.seg, d4, lane);
+            // the epilogue rows of the NEXT segment (its own X row for the fused self-loop term, its sqrt(deg)) are pulled towards L2 now:
+            // they are read at the very end of a segment and used at once, i.e. at full DRAM latency otherwise
+            if (p.T) {
+                const int lines = (row_f * 4 + 127) >> 7;
+                if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.Xself + (size_t)nxt.seg * row_f + lane * 32));
+            }
+            if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sqrt_deg + nxt.seg));
         }
         float m = -INFINITY, l = 0.f;
         Row<VPL> acc;
