@@ -936,7 +936,7 @@ def run_b200(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this same workload
 # (bytes): Zipf graph -- profiles/ncu_edge_kernels_r02.md; uniform graph -- profiles/ncu_edge_kernels_r01.md
-TRAFFIC_NCU = {"zipf": {"edge_fwd": 91.21e9, "edge_bwd_dst": 50.84e9, "edge_bwd_src": 38.39e9, "edge_bwd_rel": 27.83e9,
+TRAFFIC_NCU = {"zipf": {"edge_fwd": 93.01e9, "edge_bwd_dst": 52.41e9, "edge_bwd_src": 38.34e9, "edge_bwd_rel": 27.81e9,
                         "source": "profiles/ncu_edge_kernels_r02.md"},
                "uniform": {"edge_fwd": 91.33e9, "edge_bwd_dst": 52.46e9, "edge_bwd_src": 56.69e9, "edge_bwd_rel": 49.99e9,
                            "source": "profiles/ncu_edge_kernels_r01.md"}}
