@@ -330,9 +330,6 @@ __global__ void __launch_bounds__(256) edge_bwd_gather_kernel(EdgeBwdGatherParam
 // ------------------------------------------------------------------------------------------------
 // ring depth by row width: 12 slots of 1 KB + mask at d <= 256, 7 / 6 for the wider rows of VPL = 3 / 4
 template <int VPL> struct BwdRing { static constexpr int S = VPL <= 2 ? 12 : (VPL == 3 ? 7 : 6); };
-// The destination pass also stages the two per-destination rows (G[i], agg[i]) of a warp's NEXT segment in shared memory (rows of
-// up to 1 KB): two ring slots per warp make room for them.
-template <int VPL> struct DstRing { static constexpr bool STAGE = VPL <= 2; static constexpr int S = STAGE ? 10 : BwdRing<VPL>::S; };
 
 template <int BWD_RING_S>
 struct Ring {
@@ -419,28 +416,9 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
     const int warp = blockIdx.x * RING_WARPS + wib;
     const int nwarps = gridDim.x * RING_WARPS;
     const int d4 = FULLROW ? VPL * 32 : p.d4;      // see edge_fwd_ring_kernel
-    constexpr int BWD_RING_S = DstRing<VPL>::S;
-    constexpr bool STAGE = DstRing<VPL>::STAGE;
+    constexpr int BWD_RING_S = BwdRing<VPL>::S;
     Ring<BWD_RING_S> ring;
     ring.init(ring_raw, wib, lane, d4, (int)sizeof(mask_t) * 32);
-    // Per-destination rows: every segment starts with G[i] and agg[i] (and their dot product, a warp reduction) before its first edge
-    // can be finished.  Loaded at the point of use they cost an L2 round trip per segment (~11 % of the warp time in the ncu source
-    // view, mean in-degree 20); here lane 0 copies the NEXT segment's two rows into a per-warp staging area (cp.async.bulk, one
-    // mbarrier) while the current segment is processed.
-    const uint8_t* stage = nullptr;
-    uint32_t stage_s = 0, stage_bar = 0, stage_phase = 0;
-    if (STAGE) {
-        const uint32_t ring_end = (uint32_t)RING_WARPS * BWD_RING_S * (ring.slot_bytes + 8);          // slots + their barriers
-        const uint32_t rows_off = ((ring_end + (uint32_t)RING_WARPS * 8 + 127u) & ~127u) + (uint32_t)wib * 2 * ring.row_bytes;
-        stage = ring_raw + rows_off;
-        stage_s = smem_addr(ring_raw) + rows_off;
-        stage_bar = smem_addr(ring_raw) + ring_end + (uint32_t)wib * 8;
-        if (lane == 0) {
-            mbar_init(stage_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
     Row<VPL> av, da_acc, gs_acc;
     load_row<VPL, false>(av, p.a, 0, d4, lane);
     da_acc.zero();
@@ -474,55 +452,29 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
             load_row<REL_AHEAD ? VPL : 1, false>(rn0, p.Rp, __shfl_sync(FULL, tv, 0), d4, lane);
             load_row<REL_AHEAD ? VPL : 1, false>(rn1, p.Rp, __shfl_sync(FULL, tv, 1), d4, lane);
         }
-        // Segment descriptors run two ahead of their use (nxt: the next item, nn_seg: the node of the one after it) and the per-segment
-        // scalars one ahead, so that nothing at a segment boundary waits for a dependent load.
-        Item nxt = it0 + 1 < it1 ? p.items[it0 + 1] : item;
-        int nn_seg = it0 + 2 < it1 ? __ldg(&p.items[it0 + 2].seg) : -1;
-        int prev_seg = it0 > 0 ? __ldg(&p.items[it0 - 1].seg) : -1;
-        float lse_n = p.lse[item.seg], c_n = p.sqrt_deg[item.seg];
-        auto stage_issue = [&](int seg) {
-            if (lane == 0) {
-                mbar_expect_tx(stage_bar, 2 * ring.row_bytes);
-                bulk_row(stage_s, p.G + (size_t)seg * ring.row_f, ring.row_bytes, stage_bar);
-                bulk_row(stage_s + ring.row_bytes, p.agg + (size_t)seg * ring.row_f, ring.row_bytes, stage_bar);
-            }
-        };
-        if (STAGE) stage_issue(item.seg);
-        prefetch_rows_l2(STAGE ? nullptr : p.G, STAGE ? nullptr : p.agg, p.P, item.seg, d4 * 4, lane);
-        if (it0 + 1 < it1) prefetch_rows_l2(p.G, p.agg, p.P, nxt.seg, d4 * 4, lane);
         for (int it = it0; it < it1; ++it) {
-            Item nxt2 = nxt;
-            int nn2 = -1;
-            if (it + 2 < it1) nxt2 = p.items[it + 2];                  // used from the next iteration on
-            if (it + 3 < it1) nn2 = __ldg(&p.items[it + 3].seg);
-            if (nn_seg >= 0) prefetch_rows_l2(p.G, p.agg, p.P, nn_seg, d4 * 4, lane);     // two segments ahead: towards L2
-            const float lse = lse_n, c = c_n;
+            Item nxt = item;
             if (it + 1 < it1) {
-                lse_n = p.lse[nxt.seg];
-                c_n = p.sqrt_deg[nxt.seg];
+                nxt = p.items[it + 1];
+                prefetch_rows_l2(p.G, p.agg, p.P, nxt.seg, d4 * 4, lane);
             }
-            Row<VPL> gi, mu, ai;
-            if (STAGE) {
-                mbar_wait(stage_bar, stage_phase);
-                stage_phase ^= 1;
-                lds_row<VPL>(gi, reinterpret_cast<const float*>(stage), d4, lane);
-                lds_row<VPL>(ai, reinterpret_cast<const float*>(stage + ring.row_bytes), d4, lane);
-                __syncwarp();                                        // every lane has its copies: the staging rows may be refilled
-                if (it + 1 < it1) stage_issue(nxt.seg);
-            } else {
-                load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
-                load_row<VPL, true>(ai, p.agg, item.seg, d4, lane);
-            }
-            if (p.gsum && item.seg != prev_seg) {                     // every destination once (first item of its segment)
+            Row<VPL> gi, mu;
+            load_row<VPL, true>(gi, p.G, item.seg, d4, lane);
+            if (p.gsum && (it == 0 || __ldg(&p.items[it - 1].seg) != item.seg)) {   // every destination once (first item of its segment)
 #pragma unroll
                 for (int i = 0; i < VPL; ++i) gs_acc.v[i] = gs_acc.v[i] + gi.v[i];
             }
-            prev_seg = item.seg;
             mu.zero();
             float gdot = 0.f, ds_sum = 0.f;
+            {
+                Row<VPL> ai;
+                load_row<VPL, true>(ai, p.agg, item.seg, d4, lane);
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) gdot += dot4(gi.v[i], ai.v[i]);
-            gdot = warp_sum(gdot);
+                for (int i = 0; i < VPL; ++i) gdot += dot4(gi.v[i], ai.v[i]);
+                gdot = warp_sum(gdot);
+            }
+            const float lse = p.lse[item.seg];
+            const float c = p.sqrt_deg[item.seg];
             for (int k = item.beg; k < item.end; k += 2) {
                 if (k - batch_base >= ADV) {                      // next index batch (warp-uniform)
                     if (batch_base + lane < k) p.ew[batch_base + lane] = make_float2(w_keep, ds_keep);
@@ -619,8 +571,6 @@ __global__ void __launch_bounds__(RING_WARPS * 32, 1) edge_bwd_dst_ring_kernel(E
             if (item.slot < 0) store_row<VPL>(mu, p.dP, item.seg, d4, lane);
             else store_row<VPL>(mu, p.partial, item.slot, d4, lane);
             item = nxt;
-            nxt = nxt2;
-            nn_seg = nn2;
         }
         if (batch_base + lane < stream_end) p.ew[batch_base + lane] = make_float2(w_keep, ds_keep);
     }
@@ -754,13 +704,6 @@ static inline int bwd_ring_depth(int d) {
     return vpl <= 2 ? BwdRing<2>::S : (vpl == 3 ? BwdRing<3>::S : BwdRing<4>::S);
 }
 static inline size_t bwd_ring_smem(int d) { return (size_t)RING_WARPS * bwd_ring_depth(d) * ((size_t)d * 4 + edge_mask_bytes(d) + 8); }
-// destination pass: its own ring depth, plus (rows of <= 1 KB) one barrier and two staged rows per warp behind the ring
-static inline size_t dst_ring_smem(int d) {
-    const int vpl = (d / 4 + 31) / 32;
-    if (vpl > 2) return bwd_ring_smem(d);
-    const size_t ring_end = (size_t)RING_WARPS * DstRing<2>::S * ((size_t)d * 4 + edge_mask_bytes(d) + 8);
-    return ((ring_end + (size_t)RING_WARPS * 8 + 127) & ~(size_t)127) + (size_t)RING_WARPS * 2 * (size_t)d * 4;
-}
 static inline bool use_ring(int d) {
     static const int on = getenv("JMAC_EDGE_RING") ? atoi(getenv("JMAC_EDGE_RING")) : 1;
     const int vpl = (d / 4 + 31) / 32;
@@ -804,9 +747,9 @@ extern "C" int jmac_edge_bwd_dst(jmac_plan* plan, const float* P, const float* X
         constexpr int U = VPL <= 2 ? 4 : 2;
         if (use_ring(d) && plan->E > 0) {
             auto kern = d == VPL * 128 ? edge_bwd_dst_ring_kernel<VPL, true> : edge_bwd_dst_ring_kernel<VPL, false>;
-            JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dst_ring_smem(d)));
+            JMAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_ring_smem(d)));
             long long want = ((long long)p.n_items + RING_WARPS - 1) / RING_WARPS;
-            kern<<<(int)(want < sm_count() ? want : sm_count()), RING_WARPS * 32, dst_ring_smem(d), st>>>(p);
+            kern<<<(int)(want < sm_count() ? want : sm_count()), RING_WARPS * 32, bwd_ring_smem(d), st>>>(p);
         } else {
             auto kern = edge_bwd_dst_kernel<VPL, U>;
             int blocks = persistent_blocks(kern, threads, p.n_items);

@@ -380,12 +380,17 @@ def sharded_layer_forward(layer, x_loc, rel_emb, shard: Shard, plan, group, ops=
     ``plan`` is the bipartite plan of shard.edge_index (n_loc destinations x world*n_max sources)."""
     ops = ops or _default_ops()
     d = layer.in_channels
-    if layer.comp_op != "sub":
+    if layer.comp_op not in ("sub", "mult"):
         raise NotImplementedError
     Rp = layer.relation_transform(rel_emb)
     x_loc = x_loc.contiguous()
     mm = getattr(ops, "node_mm", torch.mm)
-    if _fused_eligible(ops, x_loc, shard, d):
+    if layer.comp_op == "mult":
+        # src/jmac_model.py:63-64 under destination sharding: the per-edge tables are built from the gathered source table for the
+        # local destinations only (model.RelationAwareLayer.mult_edge_phase); the exchange is the same all-gather / reduce-scatter
+        Xf = GatherRowsFn.apply(x_loc, shard, group, x_full)
+        T = layer.mult_edge_phase(x_loc, Xf, Rp, shard.edge_index, shard.edge_type)
+    elif _fused_eligible(ops, x_loc, shard, d):
         T = ShardedAttnEdgeFn.apply(plan, x_loc, x_full, layer.w_att, Rp, layer.a_att, layer.leaky_slope, shard, group)
     else:
         # small shards (library GEMMs) and the CPU stand-ins of the gloo tests: the same algebra through autograd --

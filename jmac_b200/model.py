@@ -121,28 +121,20 @@ class RelationAwareLayer(nn.Module):
 
     def forward_mult(self, ent_emb, rel_emb, edge_index, edge_type):
         """comp_op='mult' (src/jmac_model.py:63-64): the composed row ``m_e = x_j * r_t`` depends on the edge, so the
-        attention product ``m_e W_bot`` cannot be hoisted to the nodes.  The per-edge table ``M[E,d]`` is materialised
-        once (gather + multiply), its attention projection is ONE E-row product on the tcgen05 3xTF32 kernel, and the
-        edge kernels run unchanged on a bipartite plan whose "sources" are the E rows of M (zero relation tables):
-        logit ``a . lrelu(P[i] + (M W_bot)[e])``, aggregate ``sqrt(deg_i) sum_e alpha_e M[e]``; the message GEMM is still
-        applied once per node after aggregation.  The self loop is ``(x_i * r_loop) W_g``.  Memory is O(E d): meant
-        for the reference's graph sizes (DBP-5L / OpenEA), not for C4."""
-        if self.dist_group is not None:
-            raise NotImplementedError("comp_op='mult' is single-GPU")
+        attention product ``m_e W_bot`` cannot be hoisted to the nodes.  The per-edge table ``M`` is materialised (gather +
+        multiply), its attention projection is ONE product on the tcgen05 3xTF32 kernel, and the edge kernels run unchanged
+        on a bipartite plan whose "sources" are the rows of M (zero relation tables): logit ``a . lrelu(P[i] + (M W_bot)[e])``,
+        aggregate ``sqrt(deg_i) sum_e alpha_e M[e]``; the message GEMM is still applied once per node after aggregation.  The
+        self loop is ``(x_i * r_loop) W_g``.  Beyond ``MULT_TABLE_BYTES`` the tables are built one block of destinations at a
+        time and recomputed in backward (``mult_edge_phase``): memory is O(block edges x d), never O(E d)."""
         if self.layer_act is not torch.tanh:
             raise NotImplementedError("the fused BN+activation kernel implements tanh (BaseModel.act, src/jmac_model.py:118)")
-        num_ent, d = ent_emb.size(0), self.in_channels
+        num_ent = ent_emb.size(0)
         Rp = self.relation_transform(rel_emb)
         X = ent_emb.contiguous()
         ei = JF.as_index(edge_index, X.device)
         et = JF.as_index(edge_type, X.device)
-        E = ei.shape[1]
-        plan = JF.get_edge_table_plan(edge_index, num_ent)
-        M = X.index_select(0, ei[1]) * Rp.index_select(0, et) if E else X.new_zeros((1, d))
-        P = JF.node_mm(X, self.w_att[:d])
-        Qm = JF.node_mm(M, self.w_att[d:])
-        zero = X.new_zeros((1, d))
-        T = JF.edge_phase(plan, P, Qm, M, zero, zero, self.a_att, self.leaky_slope, X * Rp[-1])
+        T = self.mult_edge_phase(X, X, Rp, ei, et)
         pre = JF.node_mm(T, self.gcn_weight * 0.5)
         training = self.training or not self.bn.track_running_stats
         if self.training and self.bn.track_running_stats:
@@ -150,6 +142,68 @@ class RelationAwareLayer(nn.Module):
         momentum = self.bn.momentum if self.bn.momentum is not None else 0.1
         return JF.bn_tanh(pre, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var, momentum, self.bn.eps,
                           training, None)
+
+    # per-edge tables of comp_op='mult' larger than this are built per block of destinations (bytes of ONE [E_block, d] fp32 table)
+    MULT_TABLE_BYTES = 1 << 30
+
+    def _mult_blocks(self, ei, et, n_dst, d):
+        """Destination blocks [lo, hi) whose in-edges fit ``MULT_TABLE_BYTES`` (a hub with more edges than that is a block of its own),
+        each with its edge selection, source rows, types and edge-table plan.  Cached per edge list."""
+        key = (ei.data_ptr(), tuple(ei.shape), ei._version, et.data_ptr(), et._version, int(n_dst), int(d), int(self.MULT_TABLE_BYTES))
+        cache = self.__dict__.setdefault("_mult_block_cache", {})
+        if key in cache:
+            return cache[key][0]
+        E = int(ei.shape[1])
+        e_max = max(1, int(self.MULT_TABLE_BYTES) // (4 * d))
+        row, col = ei[0], ei[1]
+        if E <= e_max:
+            blocks = [(0, n_dst, None, col, et, JF.get_edge_table_plan(ei, n_dst))]
+        else:
+            cum = torch.cumsum(torch.bincount(row, minlength=n_dst), 0).cpu()
+            bounds, done = [0], 0
+            while bounds[-1] < n_dst:
+                b = int(torch.searchsorted(cum, torch.tensor(done + e_max), right=True))      # first node whose cumulative count exceeds the budget
+                b = min(max(b, bounds[-1] + 1), n_dst)
+                bounds.append(b)
+                done = int(cum[b - 1])
+            blocks = []
+            for lo, hi in zip(bounds, bounds[1:]):
+                sel = torch.nonzero((row >= lo) & (row < hi)).reshape(-1)
+                ei_b = torch.stack([row[sel] - lo, torch.arange(sel.numel(), device=ei.device)])
+                plan = JF.GraphPlan(ei_b, torch.zeros(sel.numel(), dtype=torch.int64, device=ei.device), hi - lo, 1, n_src=max(int(sel.numel()), 1))
+                blocks.append((lo, hi, sel, col[sel], et[sel], plan))
+        cache.clear()                                             # one edge list at a time
+        cache[key] = (blocks, ei, et)
+        return blocks
+
+    def mult_edge_phase(self, X_dst, X_src, Rp, ei, et):
+        """T = sqrt(deg_i) sum_e alpha_e (x_j * r_t) + x_i * r_loop for the destinations ``X_dst`` (rows ei[0]) with sources
+        ``X_src`` (rows ei[1]; the same table on one GPU, the gathered table under destination sharding)."""
+        d = self.in_channels
+        n_dst = X_dst.size(0)
+        Wt, Wb = self.w_att[:d], self.w_att[d:]
+        P = JF.node_mm(X_dst, Wt)
+        blocks = self._mult_blocks(ei, et, n_dst, d)
+        slope = self.leaky_slope
+
+        def run(plan, col_b, et_b, P_b, Xd_b, X_src, Rp, Wb, a_att):
+            if col_b.numel():
+                M = X_src.index_select(0, col_b) * Rp.index_select(0, et_b)
+            else:
+                M = X_src.new_zeros((1, d))
+            Qm = JF.node_mm(M, Wb)
+            zero = X_src.new_zeros((1, d))
+            return JF.edge_phase(plan, P_b, Qm, M, zero, zero, a_att, slope, Xd_b * Rp[-1])
+
+        if len(blocks) == 1:
+            lo, hi, _, col_b, et_b, plan = blocks[0]
+            return run(plan, col_b, et_b, P, X_dst, X_src, Rp, Wb, self.a_att)
+        from torch.utils.checkpoint import checkpoint
+        outs = []
+        for lo, hi, _, col_b, et_b, plan in blocks:
+            # the block's [E_block, d] tables live only inside this call, forward and (recomputed) backward
+            outs.append(checkpoint(run, plan, col_b, et_b, P[lo:hi], X_dst[lo:hi], X_src, Rp, Wb, self.a_att, use_reentrant=False))
+        return torch.cat(outs, dim=0)
 
 
 class BaseModel(nn.Module):

@@ -105,6 +105,8 @@ def _worker(rank, world, port, N, E, R, d, chunks, exchange="nccl"):
             # float64, and within 1e-2 of the single-GPU result itself.
             err_new, err_ref, err_one = _rel_err(got, ref64), _rel_err(ref32, ref64), _rel_err(one_gpu, ref64)
             tol = max(1e-4, 4 * err_ref)
+            print(f"[rank {rank} {exchange}] {name}: sharded {err_new:.2e}, single GPU {err_one:.2e}, reference-fp32 {err_ref:.2e} from float64; "
+                  f"sharded vs single GPU {_rel_err(got, one_gpu):.2e}", file=sys.stderr, flush=True)
             assert err_new <= tol or err_new <= 2 * max(tol, err_one), f"{name}: {err_new:.2e} vs reference-fp32 {err_ref:.2e}, single GPU {err_one:.2e}"
             assert _rel_err(got, one_gpu) <= 1e-2, f"{name}: {_rel_err(got, one_gpu):.2e} from the single-GPU path"
 
@@ -163,6 +165,54 @@ def test_sharded_encoder_peer_exchange_matches_oracle(N, E, chunks):
                                         (40000, 250001, None)])  # default chunking (4)
 def test_sharded_encoder_matches_oracle_nccl(N, E, chunks):
     mp.spawn(_worker, args=(2, _free_port(), N, E, 30, 256, chunks), nprocs=2, join=True)
+
+
+def _mult_worker(rank, world, port, N, E, R, d):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), JMAC_DIST_PEER="0")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
+    try:
+        from jmac_b200 import dist as JD
+        rng = np.random.default_rng(2)
+        row, col, typ = rng.integers(0, N, E), rng.integers(0, N, E), rng.integers(0, R, E)
+        row[: E // 6] = 5
+        ei, et = torch.from_numpy(np.stack([row, col])).to(dev), torch.from_numpy(typ).to(dev)
+        torch.manual_seed(1)
+        x, rel, gout = (torch.randn(N, d) * 0.5).to(dev), (torch.randn(R, d) * 0.5).to(dev), torch.randn(N, d).to(dev)
+
+        def layers():
+            ls = [l.to(dev) for l in _make_layers(d)]
+            for l in ls:
+                l.comp_op = "mult"
+            return ls
+        single = layers()
+        xs, rs = x.clone().requires_grad_(True), rel.clone().requires_grad_(True)
+        hs = single[1](single[0](xs, rs, ei, et), rs, ei, et)
+        hs.backward(gout)
+        ls = layers()
+        enc = JD.ShardedEncoder(ls, ei, et, N, R, dist.group.WORLD)
+        rg = rel.clone().requires_grad_(True)
+        out = enc.step(x, rg, gout)
+        sh = enc.shard
+        torch.testing.assert_close(out, hs.detach()[sh.lo:sh.hi], atol=1e-4, rtol=1e-4)
+        assert _rel_err(enc._x_loc.grad, xs.grad[sh.lo:sh.hi]) < 1e-3
+        assert _rel_err(rg.grad, rs.grad) < 1e-3
+        for l, l1 in zip(ls, single):
+            one = dict(l1.named_parameters())
+            for k, v in l.named_parameters():
+                if k != "loop_rel":
+                    assert _rel_err(v.grad, one[k].grad) < 1e-3, k
+        enc.close()
+    except BaseException:
+        _die()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_mult_encoder_matches_single_gpu_nccl():
+    """comp_op='mult' (src/jmac_model.py:63-64) destination-sharded: per-edge tables from the gathered source table, local destinations only."""
+    mp.spawn(_mult_worker, args=(2, _free_port(), 6000, 40000, 12, 64), nprocs=2, join=True)
 
 
 def _align_worker(rank, world, port, n1, n2, d, csls):
