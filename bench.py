@@ -380,7 +380,8 @@ def multi_gpu_parity(dev, world, group):
     base = [RelationAwareLayer(D, D, rel_dim=D, act=torch.tanh, args=largs).to(dev) for _ in range(2)]
 
     def rerr(a, b):
-        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        a, b = a.detach().double(), b.detach().double()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
     # (b) float64 oracle
     p64 = [{k: v.detach().double().clone().requires_grad_(True) for k, v in l.named_parameters()} for l in base]
     xo, ro = x.double().requires_grad_(True), rel.double().requires_grad_(True)
