@@ -6,8 +6,8 @@
 // (B+N)*d*4 per layer): FP32-pipe bound, not HBM bound, and not expressible on tensor cores.
 // Tile: 128 queries x 128 candidates per CTA, 8x8 register micro-tile per thread, the feature
 // dimension staged through shared memory 16 features at a time (transposed, padded).
-// Every distance -- tile kernel, target prologue, filter epilogue -- is accumulated feature by
-// feature in the same order, layer after layer, so equal inputs give bit-equal distances.
+// Every distance -- tile kernel, target prologue, filter epilogue -- is ONE running fp32 sum over the
+// features of all layers in the same order, so equal inputs give bit-equal distances.
 #include <math.h>
 
 #include "common.cuh"
@@ -32,19 +32,17 @@ struct L1Params {
 
 // sequential reference-order distance of query b to candidate n (used by prologue / filter)
 __device__ __forceinline__ float l1_seq(const L1Params& p, int64_t e, int64_t r, int64_t n) {
-    float total = 0.f;
+    float acc = 0.f;                     // one running sum over the features of all layers, in layer order
     for (int l = 0; l < p.n_layers; ++l) {
         const float* er = p.ent[l] + e * p.d;
         const float* rr = p.rel[l] + r * p.d;
         const float* cn = p.ent[l] + n * p.d;
-        float acc = 0.f;
         for (int k = 0; k < p.d; ++k) {
             const float q = __fadd_rn(er[k], p.sign * rr[k]);
             acc = __fadd_rn(acc, fabsf(__fadd_rn(q, -cn[k])));
         }
-        total = __fadd_rn(total, acc);
     }
-    return total;
+    return acc;
 }
 
 __global__ void l1_target_kernel(L1Params p, float* __restrict__ tdist, int* __restrict__ rank) {
@@ -74,66 +72,78 @@ __global__ void l1_filter_kernel(L1Params p, const int64_t* __restrict__ filt_pt
 }
 
 template <bool RANK>
-__global__ void __launch_bounds__(256) l1_tile_kernel(L1Params p) {
+__global__ void __launch_bounds__(256, 2) l1_tile_kernel(L1Params p) {
     __shared__ float Qs[DK][PADW];
     __shared__ float Cs[DK][PADW];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t q0 = (int64_t)blockIdx.y * TQ, c0 = (int64_t)blockIdx.x * TC;
+    // One accumulator per (query, candidate) of the 8x8 micro-tile, running over the features of all layers (64 registers; a
+    // per-layer sum next to a total would make it 128 and halve the occupancy), two CTAs per SM.
     float total[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) total[i][j] = 0.f;
 
-    // loader mapping: 128 rows x 4 float4 per chunk = 512 float4, two per thread
+    // loader mapping: 128 rows x 4 float4 per chunk = 512 float4, two per thread.  The rows a thread loads never change: their table
+    // rows are looked up once (the index -> row -> data chain used to be walked at every stage), and the loads of stage s + 1 are issued
+    // into registers before the arithmetic of stage s, so that their latency hides behind it.
     const int lrow = threadIdx.x >> 2, lk4 = threadIdx.x & 3;
-    for (int l = 0; l < p.n_layers; ++l) {
+    int64_t erow[2], rrow[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int64_t b = q0 + lrow + half * 64;
+        erow[half] = b < p.B ? safe_index(p.e_idx[b], p.N, p.status) : -1;
+        rrow[half] = b < p.B ? safe_index(p.r_idx[b], p.n_rel, p.status) : 0;
+    }
+    const int spl = (p.d + DK - 1) / DK;                 // stages per layer
+    const int n_stages = p.n_layers * spl;
+    float4 qn[2], cn[2];
+    auto fetch = [&](int s) {
+        const int l = s / spl, kk = (s - l * spl) * DK + lk4 * 4;
         const float* ent = p.ent[l];
         const float* rel = p.rel[l];
-        float acc[8][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-        for (int k0 = 0; k0 < p.d; k0 += DK) {
-            __syncthreads();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int row = lrow + half * 64;
-                const int kk = k0 + lk4 * 4;
-                float4 qv = f4_zero(), cv = f4_zero();
-                if (kk < p.d) {
-                    if (q0 + row < p.B) {
-                        const float4 ev = __ldg(reinterpret_cast<const float4*>(ent + safe_index(p.e_idx[q0 + row], p.N, p.status) * p.d + kk));
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rel + safe_index(p.r_idx[q0 + row], p.n_rel, p.status) * p.d + kk));
-                        qv = make_float4(__fadd_rn(ev.x, p.sign * rv.x), __fadd_rn(ev.y, p.sign * rv.y), __fadd_rn(ev.z, p.sign * rv.z),
-                                         __fadd_rn(ev.w, p.sign * rv.w));
-                    }
-                    if (c0 + row < p.N) cv = __ldg(reinterpret_cast<const float4*>(ent + (c0 + row) * p.d + kk));
+        for (int half = 0; half < 2; ++half) {
+            const int row = lrow + half * 64;
+            qn[half] = f4_zero();
+            cn[half] = f4_zero();
+            if (kk < p.d) {
+                if (erow[half] >= 0) {
+                    const float4 ev = __ldg(reinterpret_cast<const float4*>(ent + erow[half] * p.d + kk));
+                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rel + rrow[half] * p.d + kk));
+                    qn[half] = make_float4(__fadd_rn(ev.x, p.sign * rv.x), __fadd_rn(ev.y, p.sign * rv.y), __fadd_rn(ev.z, p.sign * rv.z),
+                                           __fadd_rn(ev.w, p.sign * rv.w));
                 }
-                Qs[lk4 * 4 + 0][row] = qv.x; Qs[lk4 * 4 + 1][row] = qv.y; Qs[lk4 * 4 + 2][row] = qv.z; Qs[lk4 * 4 + 3][row] = qv.w;
-                Cs[lk4 * 4 + 0][row] = cv.x; Cs[lk4 * 4 + 1][row] = cv.y; Cs[lk4 * 4 + 2][row] = cv.z; Cs[lk4 * 4 + 3][row] = cv.w;
-            }
-            __syncthreads();
-            const int kmax = min(DK, p.d - k0);
-            for (int k = 0; k < kmax; ++k) {
-                // micro-tile rows/cols {4t..4t+3} and {64+4t..64+4t+3}: conflict-free LDS.128
-                const float4 qa = *reinterpret_cast<const float4*>(&Qs[k][ty * 4]);
-                const float4 qb = *reinterpret_cast<const float4*>(&Qs[k][64 + ty * 4]);
-                const float4 ca = *reinterpret_cast<const float4*>(&Cs[k][tx * 4]);
-                const float4 cb = *reinterpret_cast<const float4*>(&Cs[k][64 + tx * 4]);
-                const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = __fadd_rn(acc[i][j], fabsf(__fadd_rn(q[i], -c[j])));
+                if (c0 + row < p.N) cn[half] = __ldg(reinterpret_cast<const float4*>(ent + (c0 + row) * p.d + kk));
             }
         }
+    };
+    fetch(0);
+    for (int s = 0; s < n_stages; ++s) {
+        __syncthreads();                                 // the previous stage's arithmetic has read the tiles
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int half = 0; half < 2; ++half) {
+            const int row = lrow + half * 64;
+            Qs[lk4 * 4 + 0][row] = qn[half].x; Qs[lk4 * 4 + 1][row] = qn[half].y; Qs[lk4 * 4 + 2][row] = qn[half].z; Qs[lk4 * 4 + 3][row] = qn[half].w;
+            Cs[lk4 * 4 + 0][row] = cn[half].x; Cs[lk4 * 4 + 1][row] = cn[half].y; Cs[lk4 * 4 + 2][row] = cn[half].z; Cs[lk4 * 4 + 3][row] = cn[half].w;
+        }
+        __syncthreads();
+        if (s + 1 < n_stages) fetch(s + 1);
+        const int kmax = min(DK, p.d - (s % spl) * DK);
+        for (int k = 0; k < kmax; ++k) {
+            // micro-tile rows/cols {4t..4t+3} and {64+4t..64+4t+3}: conflict-free LDS.128
+            const float4 qa = *reinterpret_cast<const float4*>(&Qs[k][ty * 4]);
+            const float4 qb = *reinterpret_cast<const float4*>(&Qs[k][64 + ty * 4]);
+            const float4 ca = *reinterpret_cast<const float4*>(&Cs[k][tx * 4]);
+            const float4 cb = *reinterpret_cast<const float4*>(&Cs[k][64 + tx * 4]);
+            const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) total[i][j] = __fadd_rn(total[i][j], acc[i][j]);
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) total[i][j] = __fadd_rn(total[i][j], fabsf(__fadd_rn(q[i], -c[j])));
+        }
     }
 
     if (!RANK) {

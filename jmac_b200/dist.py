@@ -470,6 +470,14 @@ class ShardedEncoder:
             return
         mine = (all(l.in_channels == d and l.comp_op == "sub" for l in self.layers) and ops._tc_eligible(sh.n_loc, d, d) and ops._tn_eligible(sh.n_loc, d, d)
                 and ops._tc_eligible(sh.world * sh.n_c, d, d) and ops._tn_eligible(sh.n_src, d, d))
+        # The handshakes park cuStreamWaitValue32 waits on the copy streams.  With the default 8 hardware work queues a copy stream can share
+        # a queue with the compute stream, and a parked wait would then hold back the very kernels the peer is waiting for: the exchange is
+        # only used when the process was started with enough queues (the variable is read when the CUDA context is created).
+        if int(_os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8") or 8) < 16 and want != "1":
+            if mine and self.rank == 0:
+                import warnings
+                warnings.warn("peer-memory exchange not used: start the process with CUDA_DEVICE_MAX_CONNECTIONS=32 (NCCL collectives instead)")
+            mine = False
         vote = torch.tensor([1.0 if mine else 0.0], device=dev)
         dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=self.group)
         if float(vote.item()) == 0.0:
