@@ -23,6 +23,20 @@ from torch.nn.init import xavier_normal_
 from . import functional as JF
 
 
+def mult_block_bounds(in_degree: torch.Tensor, e_max: int) -> List[int]:
+    """Boundaries 0 = b[0] < b[1] < ... = N of consecutive destination blocks with at most ``e_max`` in-edges each; a node with more
+    in-edges than that is a block of its own (comp_op='mult': the per-edge tables are built one block at a time)."""
+    n = int(in_degree.numel())
+    cum = torch.cumsum(in_degree.to(torch.int64), 0)
+    bounds, done = [0], 0
+    while bounds[-1] < n:
+        b = int(torch.searchsorted(cum, torch.tensor(done + int(e_max), dtype=torch.int64), right=True))   # first node whose cumulative count exceeds the budget
+        b = min(max(b, bounds[-1] + 1), n)
+        bounds.append(b)
+        done = int(cum[b - 1])
+    return bounds
+
+
 def get_param(shape):
     """modules/helper/helper.py:68-74 -- xavier_normal_ initialised Parameter."""
     param = nn.Parameter(torch.empty(*shape))
@@ -159,13 +173,7 @@ class RelationAwareLayer(nn.Module):
         if E <= e_max:
             blocks = [(0, n_dst, None, col, et, JF.get_edge_table_plan(ei, n_dst))]
         else:
-            cum = torch.cumsum(torch.bincount(row, minlength=n_dst), 0).cpu()
-            bounds, done = [0], 0
-            while bounds[-1] < n_dst:
-                b = int(torch.searchsorted(cum, torch.tensor(done + e_max), right=True))      # first node whose cumulative count exceeds the budget
-                b = min(max(b, bounds[-1] + 1), n_dst)
-                bounds.append(b)
-                done = int(cum[b - 1])
+            bounds = mult_block_bounds(torch.bincount(row, minlength=n_dst).cpu(), e_max)
             blocks = []
             for lo, hi in zip(bounds, bounds[1:]):
                 sel = torch.nonzero((row >= lo) & (row < hi)).reshape(-1)
