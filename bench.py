@@ -931,6 +931,7 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        runner.close()                       # peer-memory buffers: released collectively, before any rank leaves
         dist.barrier()
         dist.destroy_process_group()
 
