@@ -77,13 +77,16 @@ def _worker(rank, world, port, N, E, R, d, chunks, exchange="nccl"):
         rg = rel.to(dev).requires_grad_(True)
         out = enc.step(x.to(dev), rg, gout.to(dev))
         if exchange == "peer":
-            # the copy-engine exchange moves the same numbers as NCCL's all-gather and adds the partials in rank order: a second and third
-            # step (slot reuse of the double-buffered peer tables) must reproduce the first (up to BatchNorm's fp64 atomics)
+            # Slot reuse of the double-buffered peer tables: three more steps, two of them on OTHER inputs, then the first input again.
+            # A pull that ran ahead of its producer (or a buffer overwritten while a peer still read it) would mix in the rows of an
+            # earlier step, which now differ; the last step must reproduce the first (up to BatchNorm's fp64 atomics).
             dx1 = enc._x_loc.grad.clone()
-            for _ in range(2):
-                out2 = enc.step(x.to(dev), rg, gout.to(dev))
-                torch.testing.assert_close(out2, out, rtol=1e-5, atol=1e-6)
-                torch.testing.assert_close(enc._x_loc.grad, dx1, rtol=1e-5, atol=1e-6 * float(dx1.abs().max()))
+            xd, gd = x.to(dev), gout.to(dev)
+            for scale in (1.7, -0.6):
+                enc.step(xd * scale + 0.1, rg, gd * scale)
+            out4 = enc.step(xd, rg, gd)
+            torch.testing.assert_close(out4, out, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(enc._x_loc.grad, dx1, rtol=1e-5, atol=1e-6 * float(dx1.abs().max()))
         sh = enc.shard
         torch.testing.assert_close(out.double(), h64[sh.lo:sh.hi], atol=1e-4, rtol=1e-4)   # two stacked layers; the hub row (sqrt(deg) = 110) amplifies fp32 path differences
 
