@@ -389,7 +389,7 @@ def sharded_layer_forward(layer, x_loc, rel_emb, shard: Shard, plan, group, ops=
         # src/jmac_model.py:63-64 under destination sharding: the per-edge tables are built from the gathered source table for the
         # local destinations only (model.RelationAwareLayer.mult_edge_phase); the exchange is the same all-gather / reduce-scatter
         Xf = GatherRowsFn.apply(x_loc, shard, group, x_full)
-        T = layer.mult_edge_phase(x_loc, Xf, Rp, shard.edge_index, shard.edge_type)
+        T = layer.mult_edge_phase(x_loc, Xf, Rp, shard.edge_index, shard.edge_type, ops)
     elif _fused_eligible(ops, x_loc, shard, d):
         T = ShardedAttnEdgeFn.apply(plan, x_loc, x_full, layer.w_att, Rp, layer.a_att, layer.leaky_slope, shard, group)
     else:

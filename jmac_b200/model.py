@@ -160,10 +160,10 @@ class RelationAwareLayer(nn.Module):
     # per-edge tables of comp_op='mult' larger than this are built per block of destinations (bytes of ONE [E_block, d] fp32 table)
     MULT_TABLE_BYTES = 1 << 30
 
-    def _mult_blocks(self, ei, et, n_dst, d):
+    def _mult_blocks(self, ei, et, n_dst, d, ops=JF):
         """Destination blocks [lo, hi) whose in-edges fit ``MULT_TABLE_BYTES`` (a hub with more edges than that is a block of its own),
         each with its edge selection, source rows, types and edge-table plan.  Cached per edge list."""
-        key = (ei.data_ptr(), tuple(ei.shape), ei._version, et.data_ptr(), et._version, int(n_dst), int(d), int(self.MULT_TABLE_BYTES))
+        key = (ei.data_ptr(), tuple(ei.shape), ei._version, et.data_ptr(), et._version, int(n_dst), int(d), int(self.MULT_TABLE_BYTES), id(ops))
         cache = self.__dict__.setdefault("_mult_block_cache", {})
         if key in cache:
             return cache[key][0]
@@ -171,27 +171,35 @@ class RelationAwareLayer(nn.Module):
         e_max = max(1, int(self.MULT_TABLE_BYTES) // (4 * d))
         row, col = ei[0], ei[1]
         if E <= e_max:
-            blocks = [(0, n_dst, None, col, et, JF.get_edge_table_plan(ei, n_dst))]
+            if ops is JF:
+                plan = JF.get_edge_table_plan(ei, n_dst)
+            else:
+                plan = ops.GraphPlan(torch.stack([row, torch.arange(E, device=ei.device)]), torch.zeros(E, dtype=torch.int64, device=ei.device), n_dst, 1,
+                                     n_src=max(E, 1))
+            blocks = [(0, n_dst, None, col, et, plan)]
         else:
             bounds = mult_block_bounds(torch.bincount(row, minlength=n_dst).cpu(), e_max)
             blocks = []
             for lo, hi in zip(bounds, bounds[1:]):
                 sel = torch.nonzero((row >= lo) & (row < hi)).reshape(-1)
                 ei_b = torch.stack([row[sel] - lo, torch.arange(sel.numel(), device=ei.device)])
-                plan = JF.GraphPlan(ei_b, torch.zeros(sel.numel(), dtype=torch.int64, device=ei.device), hi - lo, 1, n_src=max(int(sel.numel()), 1))
+                plan = ops.GraphPlan(ei_b, torch.zeros(sel.numel(), dtype=torch.int64, device=ei.device), hi - lo, 1, n_src=max(int(sel.numel()), 1))
                 blocks.append((lo, hi, sel, col[sel], et[sel], plan))
         cache.clear()                                             # one edge list at a time
         cache[key] = (blocks, ei, et)
         return blocks
 
-    def mult_edge_phase(self, X_dst, X_src, Rp, ei, et):
+    def mult_edge_phase(self, X_dst, X_src, Rp, ei, et, ops=None):
         """T = sqrt(deg_i) sum_e alpha_e (x_j * r_t) + x_i * r_loop for the destinations ``X_dst`` (rows ei[0]) with sources
-        ``X_src`` (rows ei[1]; the same table on one GPU, the gathered table under destination sharding)."""
+        ``X_src`` (rows ei[1]; the same table on one GPU, the gathered table under destination sharding).  ``ops``: the compute
+        backend (``jmac_b200.functional``; the gloo tests inject torch stand-ins)."""
+        ops = ops or JF
+        node_mm = getattr(ops, "node_mm", torch.mm)
         d = self.in_channels
         n_dst = X_dst.size(0)
         Wt, Wb = self.w_att[:d], self.w_att[d:]
-        P = JF.node_mm(X_dst, Wt)
-        blocks = self._mult_blocks(ei, et, n_dst, d)
+        P = node_mm(X_dst, Wt)
+        blocks = self._mult_blocks(ei, et, n_dst, d, ops)
         slope = self.leaky_slope
 
         def run(plan, col_b, et_b, P_b, Xd_b, X_src, Rp, Wb, a_att):
@@ -199,9 +207,9 @@ class RelationAwareLayer(nn.Module):
                 M = X_src.index_select(0, col_b) * Rp.index_select(0, et_b)
             else:
                 M = X_src.new_zeros((1, d))
-            Qm = JF.node_mm(M, Wb)
+            Qm = node_mm(M, Wb)
             zero = X_src.new_zeros((1, d))
-            return JF.edge_phase(plan, P_b, Qm, M, zero, zero, a_att, slope, Xd_b * Rp[-1])
+            return ops.edge_phase(plan, P_b, Qm, M, zero, zero, a_att, slope, Xd_b * Rp[-1])
 
         if len(blocks) == 1:
             lo, hi, _, col_b, et_b, plan = blocks[0]

@@ -72,6 +72,53 @@ class CpuOps:
         return torch.stack([O.transe_margin(e, rl, h, r, t, batch_size, margin)[0].reshape(()) for e, rl in zip(ents, rels)])
 
 
+def _mult_worker(rank, world, port, N, E, R, d, table_bytes):
+    """comp_op='mult' (src/jmac_model.py:63-64) destination-sharded: per-edge tables from the gathered source table, whole or per
+    block of destinations with recomputation in backward; compared with the single-process oracle in float64."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from jmac_b200 import dist as JD
+        torch.set_num_threads(1)
+        rng = np.random.default_rng(4)
+        row, col, typ = rng.integers(0, N, E), rng.integers(0, N, E), rng.integers(0, R, E)
+        row[: E // 4] = 2
+        ei, et = torch.from_numpy(np.stack([row, col])), torch.from_numpy(typ)
+        torch.manual_seed(2)
+        x, rel, gout = (torch.randn(N, d, dtype=torch.float64) for N, d in ((N, d), (R, d), (N, d)))
+        layers = [make_layer(d, 20), make_layer(d, 21)]
+        for l in layers:
+            l.comp_op = "mult"
+            l.MULT_TABLE_BYTES = table_bytes
+        p = [{k: v.detach().clone().requires_grad_(True) for k, v in l.named_parameters()} for l in layers]
+        xo, ro = x.clone().requires_grad_(True), rel.clone().requires_grad_(True)
+        h = xo
+        for pl in p:
+            h = O.relation_aware_layer(pl, h, ro, ei, et, slope=0.05, comp_op="mult", bn_state=None, training=True)
+        h.backward(gout)
+        enc = JD.ShardedEncoder(layers, ei, et, N, R, dist.group.WORLD, ops=CpuOps, chunks=1)
+        sh = enc.shard
+        relg = rel.clone().requires_grad_(True)
+        out = enc.step(x, relg, gout)
+        if table_bytes < 1 << 20:
+            assert len(layers[0]._mult_blocks(sh.edge_index, sh.edge_type, sh.n_loc, d, CpuOps)) > 1       # the blocked path really ran
+        np.testing.assert_allclose(out.detach().numpy(), h.detach().numpy()[sh.lo:sh.hi], atol=1e-10)
+        np.testing.assert_allclose(enc._x_loc.grad.numpy(), xo.grad.numpy()[sh.lo:sh.hi], atol=1e-9)
+        np.testing.assert_allclose(relg.grad.numpy(), ro.grad.numpy(), atol=1e-9)
+        for l, pl in zip(layers, p):
+            for k, v in l.named_parameters():
+                ref = pl[k].grad if pl[k].grad is not None else torch.zeros_like(pl[k])
+                got = v.grad if v.grad is not None else torch.zeros_like(v)
+                np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-9, err_msg=k)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("table_bytes", [1 << 30, 40 * 4 * 8])         # whole per-edge table; blocks of <= 40 edges
+def test_sharded_mult_encoder_matches_oracle_gloo(table_bytes):
+    mp.spawn(_mult_worker, args=(2, _free_port(), 60, 400, 5, 8, table_bytes), nprocs=2, join=True)
+
+
 def make_layer(d, seed):
     from types import SimpleNamespace
     from jmac_b200.model import RelationAwareLayer
