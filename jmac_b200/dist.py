@@ -497,7 +497,7 @@ class ShardedEncoder:
         if peer is not None:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)           # nobody may still be pulling from the buffers freed below
-            peer.close()
+            peer.close(collective=True)
 
     def forward(self, x_loc, rel_emb, x_full=None):
         """``x_full``: the replicated input table, if every rank holds it (saves the first all-gather)."""

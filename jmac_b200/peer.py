@@ -73,17 +73,28 @@ class PeerBuf:
         t._jmac_owner = self                     # the view must not outlive the allocation
         return t
 
-    def close(self):
+    def close_imports(self):
+        """Unmap the other ranks' copies (an exporter must not free its allocation while an importer still has it mapped)."""
         try:
             with torch.cuda.device(self.device):
                 for p in self._opened:
                     self.lib.jmac_ipc_close(ctypes.c_void_p(p))
                 self._opened = []
+        except Exception:
+            pass
+
+    def free_local(self):
+        try:
+            with torch.cuda.device(self.device):
                 if self.local:
                     self.lib.jmac_peer_free(self.local)
                     self.local = ctypes.c_void_p()
         except Exception:
             pass
+
+    def close(self):
+        self.close_imports()
+        self.free_local()
 
 
 class PeerExchange:
@@ -271,10 +282,19 @@ class PeerExchange:
                                              self.world, per, rows * self.d, 1, st), "jmac_peer_sum")
         return acc
 
-    def close(self):
-        for b in self.bufs:
-            b.close()
-        self.bufs = []
+    def close(self, collective: bool = False):
+        """Release the buffers.  ``collective``: every rank of the group calls this at the same point; the mappings of the other ranks'
+        buffers are closed everywhere (barrier) before any rank frees its own allocations."""
+        bufs, self.bufs = self.bufs, []
+        for b in bufs:
+            b.close_imports()
+        if collective and bufs:
+            try:
+                dist.barrier(group=self.group)
+            except Exception:
+                pass
+        for b in bufs:
+            b.free_local()
 
     def __del__(self):
         try:
